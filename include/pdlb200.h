@@ -1,0 +1,177 @@
+/*
+ * pdlb200.h — C-ABI of libpdlb200: the B200 (sm_100a) implementation of PDL's
+ * PP-generated broadcast-loop hot path (PDL::Ops elementwise ops, PDL::Ufunc
+ * reductions, PDL::Primitive::matmult).
+ *
+ * The boundary this library replaces is the reference's
+ *     pdl_error (*readdata)(pdl_trans *)            lib/PDL/Core/pdl.h.PL:381-403
+ * called from pdl__ensure_trans                      lib/PDL/Core/pdlapi.c:9-39,91-119
+ * One call of pdlb200_readdata() == one call of a generated pdl_<op>_readdata().
+ * The caller (an XS/PP shim that includes pdl.h; or the
+ * Python mirror in pdl_b200/) copies the fields of pdl_trans it has already
+ * computed (type_coerce + redodims done, every parameter physvaffine) into the
+ * POD descriptor below.  Nothing here includes Perl, PDL or torch headers.
+ *
+ * Memory model: every `data` pointer is a DEVICE pointer (cudaMalloc'd, or any
+ * allocation the CUDA context can address).  The library never frees or
+ * reallocates a parameter buffer.  Launches are asynchronous on `stream`.
+ * There is no CPU fallback: without a usable GPU every compute entry point
+ * returns PDLB200_ENODEVICE and fills the error buffer.
+ */
+#ifndef PDLB200_H
+#define PDLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PDLB200_API __attribute__((visibility("default")))
+#else
+#define PDLB200_API
+#endif
+
+#define PDLB200_ABI_VERSION 1
+
+/* Element types: numeric values are PDL's own pdl_datatypes enum
+ * (lib/PDL/Types.pm:27-255, order is significant for promotion).
+ * LD/CF/CD/CLD (11..14) are not implemented on the device: LD/CLD are x87
+ * 80-bit and have no GPU representation. */
+enum {
+  PDLB200_SB = 0, PDLB200_B = 1, PDLB200_S = 2, PDLB200_US = 3, PDLB200_L = 4,
+  PDLB200_UL = 5, PDLB200_IND = 6, PDLB200_ULL = 7, PDLB200_LL = 8,
+  PDLB200_F = 9, PDLB200_D = 10,
+  PDLB200_NTYPES = 11
+};
+
+/* Operations.  Each names the reference pp_def whose readdata it replaces. */
+enum {
+  /* biop(), lib/PDL/Ops.pd:104-153,288-313 : a(); b(); [o]c() */
+  PDLB200_OP_PLUS = 0, PDLB200_OP_MULT, PDLB200_OP_MINUS, PDLB200_OP_DIVIDE,
+  PDLB200_OP_GT, PDLB200_OP_LT, PDLB200_OP_LE, PDLB200_OP_GE, PDLB200_OP_EQ, PDLB200_OP_NE,
+  PDLB200_OP_SHIFTLEFT, PDLB200_OP_SHIFTRIGHT, PDLB200_OP_OR2, PDLB200_OP_AND2, PDLB200_OP_XOR,
+  /* bifunc(), lib/PDL/Ops.pd:164-219,321-324 : a(); b(); [o]c() */
+  PDLB200_OP_POWER = 15, PDLB200_OP_ATAN2, PDLB200_OP_MODULO, PDLB200_OP_SPACESHIP,
+  /* ufunc() and friends, lib/PDL/Ops.pd:222-265,327-397,491-503 : a(); [o]b() */
+  PDLB200_OP_BITNOT = 19, PDLB200_OP_SQRT, PDLB200_OP_SIN, PDLB200_OP_COS, PDLB200_OP_NOT,
+  PDLB200_OP_EXP, PDLB200_OP_LOG, PDLB200_OP_LOG10, PDLB200_OP_RABS, PDLB200_OP_ASSGN,
+  PDLB200_OP_ABS2,
+  /* reductions, lib/PDL/Ufunc.pd:88-118,413-444,446-500 : a(n); [o]b() */
+  PDLB200_OP_SUMOVER = 30, PDLB200_OP_PRODOVER, PDLB200_OP_DSUMOVER, PDLB200_OP_DPRODOVER,
+  PDLB200_OP_AVERAGE, PDLB200_OP_DAVERAGE, PDLB200_OP_MINIMUM, PDLB200_OP_MAXIMUM,
+  PDLB200_OP_MINIMUM_IND, PDLB200_OP_MAXIMUM_IND,
+  /* more a(n); [o]b() reductions, lib/PDL/Ufunc.pd:143-187 */
+  PDLB200_OP_ANDOVER = 40, PDLB200_OP_OROVER, PDLB200_OP_BANDOVER, PDLB200_OP_BOROVER,
+  PDLB200_OP_ZCOVER, PDLB200_OP_XOROVER, PDLB200_OP_BXOROVER,
+  /* scans, lib/PDL/Ufunc.pd:120-141 : a(n); [o]b(n) */
+  PDLB200_OP_CUMUSUMOVER = 50, PDLB200_OP_CUMUPRODOVER, PDLB200_OP_DCUMUSUMOVER, PDLB200_OP_DCUMUPRODOVER,
+  /* matmult, lib/PDL/Primitive.pd:191-264 : a(t,h); b(w,t); [o]c(w,h) */
+  PDLB200_OP_MATMULT = 60,
+  /* type conversion, lib/PDL/Core/pdlconv.c:45-126,163-201 (converttypei) : a(); [o]b() of another type */
+  PDLB200_OP_CONVERT = 61,
+  PDLB200_OP__END
+};
+
+#define PDLB200_MAXDIMS 16  /* broadcast dims carried per call (pdl_broadcast.ndims) */
+#define PDLB200_MAXPDLS 4   /* parameters per transformation on this path (<= 3 used) */
+
+/* pdlb200_par.flags */
+#define PDLB200_PAR_BADFLAG 1  /* pdl->state & PDL_BADVAL                  pdl.h.PL:560-561 */
+#define PDLB200_PAR_BADNAN  2  /* the parameter's badvalue is NaN          pdlcore.h:202-205 */
+
+/* One parameter (ndarray) of the transformation, after make_physvaffine:
+ * element (i0,i1,...; n) lives at  data + (offs + sum_k i_k*incs[k][p] + n*inc_n) * sizeof(type)
+ * (lib/PDL/Core/pdlbroadcast.h:64, pdl.h.PL:511-517 PDL_REPRP/PDL_REPROFFS). */
+typedef struct pdlb200_par {
+  void    *data;    /* device pointer: PDL_REPRP(pdl) */
+  int64_t  offs;    /* PDL_REPROFFS(pdl), in elements */
+  uint64_t badval;  /* bit pattern of this parameter's badvalue, in `type`, low-order bytes */
+  int32_t  type;    /* PDLB200_* element type of this parameter */
+  int32_t  flags;   /* PDLB200_PAR_* */
+} pdlb200_par;
+
+/* POD image of the parts of pdl_trans + pdl_broadcast a readdata reads
+ * (lib/PDL/Core/pdl.h.PL:381-403,471-482; lib/PDL/Core/pdlbroadcast.h:18-37). */
+typedef struct pdlb200_trans {
+  int32_t op;        /* PDLB200_OP_* */
+  int32_t datatype;  /* trans->__datatype: the generic type the loop is instantiated for */
+  int32_t bvalflag;  /* trans->bvalflag: any input had PDL_BADVAL (pdlapi.c:760-766) */
+  int32_t npdls;     /* vtable->npdls */
+  int32_t ndims;     /* broadcast.ndims (0 allowed) */
+  int32_t reserved;
+  int64_t dims[PDLB200_MAXDIMS];                    /* broadcast.dims */
+  int64_t incs[PDLB200_MAXDIMS * PDLB200_MAXPDLS];  /* broadcast.incs[d*npdls + p], elements */
+  /* Named ("real") dims.  reductions/scans: n_size = ind[0], inc_a_n = rinc[0],
+   * (scans: inc_b_n = rinc[1]).  matmult: ind = {t, h, w} sizes and
+   * rinc = {inc_a_t, inc_a_h, inc_b_w, inc_b_t, inc_c_w, inc_c_h}
+   * (the generated code reads them as ind_sizes[]/inc_sizes[PDL_INC_ID()]). */
+  int64_t ind[4];
+  int64_t rinc[8];
+  pdlb200_par pdls[PDLB200_MAXPDLS];                /* inputs first, then outputs */
+  void   *stream;    /* cudaStream_t to launch on; NULL = legacy default stream */
+} pdlb200_trans;
+
+/* Return codes.  Non-zero => `err` (if given) holds a NUL-terminated message the
+ * shim turns into PDL->make_error(PDL_EUSERERROR|PDL_EFATAL, ...)  pdlutil.c:27-58 */
+enum {
+  PDLB200_OK = 0,
+  PDLB200_EINVAL = 1,     /* malformed descriptor (user error) */
+  PDLB200_EUNSUPPORTED = 2, /* op/type combination not on the device path */
+  PDLB200_ENODEVICE = 3,  /* no CUDA device / driver */
+  PDLB200_ECUDA = 4       /* CUDA runtime error */
+};
+
+/* --- the hot path ------------------------------------------------------- */
+/* Replaces pdl_<op>_readdata for every PDLB200_OP_*; dispatches to the three
+ * family launchers below. */
+PDLB200_API int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen);
+/* Ops.pd biop/bifunc/ufunc bodies on the broadcast loop. */
+PDLB200_API int pdlb200_elementwise(const pdlb200_trans *t, char *err, size_t errlen);
+/* Ufunc.pd a(n) reductions and scans. */
+PDLB200_API int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen);
+/* Primitive.pd matmult. */
+PDLB200_API int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen);
+
+/* --- device data store (north-star subsystem 1) ---------------------------
+ * Replaces pdl_allocdata (pdlapi.c:172-209) / pdl__free data (pdlapi.c:283-316)
+ * for device-resident ndarrays: a stream-ordered pool, no zero-fill (every
+ * kernel overwrites its whole output), lazy host sync by dirty bits. */
+typedef struct pdlb200_buf pdlb200_buf;
+PDLB200_API int    pdlb200_buf_new(size_t nbytes, pdlb200_buf **out, char *err, size_t errlen);
+PDLB200_API void   pdlb200_buf_free(pdlb200_buf *b);
+PDLB200_API size_t pdlb200_buf_nbytes(const pdlb200_buf *b);
+/* Device pointer, valid for the buffer's lifetime.  for_write marks the device
+ * copy newer than the host's. */
+PDLB200_API void  *pdlb200_buf_devptr(pdlb200_buf *b, int for_write);
+/* Host -> device: upload `nbytes` from `host` (marks device copy current). */
+PDLB200_API int    pdlb200_buf_upload(pdlb200_buf *b, const void *host, size_t nbytes, void *stream, char *err, size_t errlen);
+/* Device -> host iff the device copy is newer (or force != 0); synchronises the stream. */
+PDLB200_API int    pdlb200_buf_download(pdlb200_buf *b, void *host, size_t nbytes, int force, void *stream, char *err, size_t errlen);
+PDLB200_API int    pdlb200_buf_device_dirty(const pdlb200_buf *b);
+
+/* --- plumbing ------------------------------------------------------------- */
+PDLB200_API int    pdlb200_abi_version(void);
+PDLB200_API int    pdlb200_device_count(void);                 /* 0 when no usable GPU */
+PDLB200_API int    pdlb200_set_device(int dev, char *err, size_t errlen);
+PDLB200_API int    pdlb200_sm_count(void);
+PDLB200_API int    pdlb200_sync(void *stream, char *err, size_t errlen);
+/* Pinned host memory for the e2e path (host<->device copies at PCIe rate). */
+PDLB200_API void  *pdlb200_host_alloc(size_t nbytes);
+PDLB200_API void   pdlb200_host_free(void *p);
+PDLB200_API int    pdlb200_memcpy_h2d(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);
+PDLB200_API int    pdlb200_memcpy_d2h(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);
+/* Number of kernels this library has launched in this process (bench "gpu_launches"). */
+PDLB200_API uint64_t pdlb200_launch_count(void);
+/* Name of the kernel variant chosen by the most recent launch on this thread (introspection,
+ * the analogue of get_autopthread_actual, lib/PDL/Core.xs:564-573). */
+PDLB200_API const char *pdlb200_last_kernel(void);
+PDLB200_API const char *pdlb200_op_name(int op);
+PDLB200_API size_t pdlb200_type_size(int type);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDLB200_H */

@@ -1,0 +1,17 @@
+"""pdl_b200 — B200-native implementation of PDL's broadcast-loop hot path
+(PDL::Ops elementwise ops, PDL::Ufunc reductions, PDL::Primitive::matmult) behind the
+reference's operator surface.  The compute lives in libpdlb200.so (hand-written
+sm_100a CUDA behind the C-ABI in include/pdlb200.h); this package is the host-side
+mirror of the reference's interface for that path.  There is no CPU fallback."""
+from . import types
+from .types import SB, B, S, US, L, UL, IND, ULL, LL, F, D
+from .engine import CudaEngine, Engine, PDLError, default_engine, set_default_engine
+from .core import PDL, pdl, zeroes, ones, sequence, null
+from .trans import run_op, run_biop, run_ufunc, as_pdl, convert_type, SPECS
+from . import ops, ufunc, primitive
+from .primitive import matmult
+
+__all__ = ["PDL", "pdl", "zeroes", "ones", "sequence", "null", "PDLError", "CudaEngine", "Engine",
+           "default_engine", "set_default_engine", "run_op", "run_biop", "run_ufunc", "as_pdl",
+           "convert_type", "SPECS", "ops", "ufunc", "primitive", "matmult", "types",
+           "SB", "B", "S", "US", "L", "UL", "IND", "ULL", "LL", "F", "D"]

@@ -1,0 +1,83 @@
+"""Build libpdlb200.so (sm_100a only) in-tree with nvcc.
+
+    python -m pdl_b200.build [--force] [--jobs N]
+
+Each .cu under csrc/ is compiled to an object (in parallel) and linked into
+pdl_b200/lib/libpdlb200.so.  -fmad=false: the reference's x86-64 build has no FMA
+contraction, and bit-exact IEEE + - * / parity depends on it.
+The CUDA runtime is linked statically so the library has no dependency on torch's
+(or Perl's) copy of libcudart.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+OBJ = HERE / "lib" / "obj"
+LIB = HERE / "lib" / "libpdlb200.so"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _stale(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -> Path:
+    OBJ.mkdir(parents=True, exist_ok=True)
+    headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "pdlb200.h"]
+    sources = sorted(CSRC.glob("*.cu"))
+    todo = []
+    for src in sources:
+        obj = OBJ / (src.stem + ".o")
+        if force or _stale(obj, [src] + headers):
+            todo.append((src, obj))
+
+    def compile_one(pair):
+        src, obj = pair
+        cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, r
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=jobs or os.cpu_count() or 4) as ex:
+            for src, r in ex.map(compile_one, todo):
+                if r.returncode != 0:
+                    sys.stderr.write(r.stdout + r.stderr)
+                    raise RuntimeError(f"nvcc failed on {src.name}")
+                if verbose or r.stderr.strip():
+                    sys.stderr.write(f"--- {src.name}\n{r.stderr}")
+    objs = [OBJ / (s.stem + ".o") for s in sources]
+    if force or todo or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+               *map(str, objs), "-Xlinker", "--exclude-libs,ALL"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link of libpdlb200.so failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--jobs", type=int, default=None)
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(a.force, a.jobs, a.verbose))

@@ -1,0 +1,256 @@
+// api.cu — the extern "C" surface of libpdlb200 (include/pdlb200.h): descriptor
+// validation, family dispatch, the device data store and plumbing.  No torch, no
+// Perl: plain pointers and sizes only.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "common.cuh"
+
+namespace pdlb200 {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local const char *g_last_kernel = "";
+static int g_sm_count = 0;
+static int g_dev_count = -1;
+static std::mutex g_mu;
+
+void note_launch(const char *name) { g_launches.fetch_add(1, std::memory_order_relaxed); g_last_kernel = name; }
+
+static int probe_devices() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_dev_count >= 0) return g_dev_count;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  g_dev_count = n;
+  return n;
+}
+
+int sm_count() {
+  if (g_sm_count > 0) return g_sm_count;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+    g_sm_count = n;
+  else
+    g_sm_count = 148;  // B200
+  return g_sm_count;
+}
+
+// scratch for two-stage reductions: one grow-only buffer per device, used in stream order.
+static void *g_scratch[16] = {nullptr};
+static size_t g_scratch_sz[16] = {0};
+void *scratch(size_t nbytes, cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_scratch_sz[dev] < nbytes) {
+    if (g_scratch[dev]) { cudaStreamSynchronize(s); cudaDeviceSynchronize(); cudaFree(g_scratch[dev]); }
+    size_t want = nbytes < (1u << 20) ? (1u << 20) : nbytes;
+    if (cudaMalloc(&g_scratch[dev], want) != cudaSuccess) { g_scratch[dev] = nullptr; g_scratch_sz[dev] = 0; return nullptr; }
+    g_scratch_sz[dev] = want;
+  }
+  return g_scratch[dev];
+}
+
+static const char *op_names[PDLB200_OP__END] = {};
+static void init_names() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+#define N(ID, S) op_names[ID] = S;
+  N(PDLB200_OP_PLUS, "plus") N(PDLB200_OP_MULT, "mult") N(PDLB200_OP_MINUS, "minus") N(PDLB200_OP_DIVIDE, "divide")
+  N(PDLB200_OP_GT, "gt") N(PDLB200_OP_LT, "lt") N(PDLB200_OP_LE, "le") N(PDLB200_OP_GE, "ge")
+  N(PDLB200_OP_EQ, "eq") N(PDLB200_OP_NE, "ne") N(PDLB200_OP_SHIFTLEFT, "shiftleft")
+  N(PDLB200_OP_SHIFTRIGHT, "shiftright") N(PDLB200_OP_OR2, "or2") N(PDLB200_OP_AND2, "and2") N(PDLB200_OP_XOR, "xor")
+  N(PDLB200_OP_POWER, "power") N(PDLB200_OP_ATAN2, "atan2") N(PDLB200_OP_MODULO, "modulo") N(PDLB200_OP_SPACESHIP, "spaceship")
+  N(PDLB200_OP_BITNOT, "bitnot") N(PDLB200_OP_SQRT, "sqrt") N(PDLB200_OP_SIN, "sin") N(PDLB200_OP_COS, "cos")
+  N(PDLB200_OP_NOT, "not") N(PDLB200_OP_EXP, "exp") N(PDLB200_OP_LOG, "log") N(PDLB200_OP_LOG10, "log10")
+  N(PDLB200_OP_RABS, "_rabs") N(PDLB200_OP_ASSGN, "assgn") N(PDLB200_OP_ABS2, "abs2")
+  N(PDLB200_OP_SUMOVER, "sumover") N(PDLB200_OP_PRODOVER, "prodover") N(PDLB200_OP_DSUMOVER, "dsumover")
+  N(PDLB200_OP_DPRODOVER, "dprodover") N(PDLB200_OP_AVERAGE, "average") N(PDLB200_OP_DAVERAGE, "daverage")
+  N(PDLB200_OP_MINIMUM, "minimum") N(PDLB200_OP_MAXIMUM, "maximum") N(PDLB200_OP_MINIMUM_IND, "minimum_ind")
+  N(PDLB200_OP_MAXIMUM_IND, "maximum_ind") N(PDLB200_OP_ANDOVER, "andover") N(PDLB200_OP_OROVER, "orover")
+  N(PDLB200_OP_BANDOVER, "bandover") N(PDLB200_OP_BOROVER, "borover") N(PDLB200_OP_ZCOVER, "zcover")
+  N(PDLB200_OP_XOROVER, "xorover") N(PDLB200_OP_BXOROVER, "bxorover")
+  N(PDLB200_OP_CUMUSUMOVER, "cumusumover") N(PDLB200_OP_CUMUPRODOVER, "cumuprodover")
+  N(PDLB200_OP_DCUMUSUMOVER, "dcumusumover") N(PDLB200_OP_DCUMUPRODOVER, "dcumuprodover")
+  N(PDLB200_OP_MATMULT, "matmult") N(PDLB200_OP_CONVERT, "converttype")
+#undef N
+}
+
+static int validate(const pdlb200_trans *t, const Err &E) {
+  if (!t) return E.fail(PDLB200_EINVAL, "pdlb200: NULL descriptor");
+  if (t->op < 0 || t->op >= PDLB200_OP__END || !pdlb200_op_name(t->op)[0])
+    return E.fail(PDLB200_EINVAL, "pdlb200: unknown op %d", t->op);
+  if (t->datatype < 0) return E.fail(PDLB200_EINVAL, "%s: invalid datatype %d", pdlb200_op_name(t->op), t->datatype);
+  if (t->datatype >= PDLB200_NTYPES)
+    return E.fail(PDLB200_EUNSUPPORTED, "%s: type %d (long double / complex) has no device representation",
+                  pdlb200_op_name(t->op), t->datatype);
+  if (t->ndims < 0 || t->ndims > PDLB200_MAXDIMS)
+    return E.fail(PDLB200_EINVAL, "%s: ndims %d out of range", pdlb200_op_name(t->op), t->ndims);
+  if (t->npdls < 2 || t->npdls > PDLB200_MAXPDLS)
+    return E.fail(PDLB200_EINVAL, "%s: npdls %d out of range", pdlb200_op_name(t->op), t->npdls);
+  for (int d = 0; d < t->ndims; d++)
+    if (t->dims[d] < 0) return E.fail(PDLB200_EINVAL, "%s: broadcast dim %d has size %lld", pdlb200_op_name(t->op), d, (long long)t->dims[d]);
+  if (probe_devices() <= 0)
+    return E.fail(PDLB200_ENODEVICE, "%s: no CUDA device available and libpdlb200 has no CPU fallback", pdlb200_op_name(t->op));
+  return PDLB200_OK;
+}
+
+int ew_arith(const pdlb200_trans *, const Err &);
+int ew_cmp(const pdlb200_trans *, const Err &);
+int ew_bits(const pdlb200_trans *, const Err &);
+int ew_func(const pdlb200_trans *, const Err &);
+int ew_unary(const pdlb200_trans *, const Err &);
+
+int launch_elementwise(const pdlb200_trans *t, const Err &E) {
+  const int op = t->op;
+  if (op <= PDLB200_OP_DIVIDE) return ew_arith(t, E);
+  if (op <= PDLB200_OP_NE) return ew_cmp(t, E);
+  if (op <= PDLB200_OP_XOR || op == PDLB200_OP_BITNOT) return ew_bits(t, E);
+  if (op <= PDLB200_OP_SPACESHIP) return ew_func(t, E);
+  if (op <= PDLB200_OP_ABS2) return ew_unary(t, E);
+  if (op == PDLB200_OP_CONVERT) return launch_convert(t, E);
+  return E.fail(PDLB200_EINVAL, "%s is not an elementwise op", pdlb200_op_name(op));
+}
+
+}  // namespace pdlb200
+
+using namespace pdlb200;
+
+extern "C" {
+
+int pdlb200_abi_version(void) { return PDLB200_ABI_VERSION; }
+int pdlb200_device_count(void) { return probe_devices(); }
+int pdlb200_sm_count(void) { return probe_devices() > 0 ? sm_count() : 0; }
+uint64_t pdlb200_launch_count(void) { return g_launches.load(); }
+const char *pdlb200_last_kernel(void) { return g_last_kernel; }
+const char *pdlb200_op_name(int op) {
+  init_names();
+  if (op < 0 || op >= PDLB200_OP__END || !op_names[op]) return "";
+  return op_names[op];
+}
+size_t pdlb200_type_size(int type) {
+  static const size_t sz[PDLB200_NTYPES] = {1, 1, 2, 2, 4, 4, 8, 8, 8, 4, 8};
+  return (type >= 0 && type < PDLB200_NTYPES) ? sz[type] : 0;
+}
+
+int pdlb200_set_device(int dev, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_set_device: no CUDA device available");
+  PDLB200_CUDA_OK(cudaSetDevice(dev), E);
+  g_sm_count = 0;
+  return PDLB200_OK;
+}
+
+int pdlb200_sync(void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_sync: no CUDA device available");
+  PDLB200_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream), E);
+  return PDLB200_OK;
+}
+
+int pdlb200_elementwise(const pdlb200_trans *t, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (int rc = validate(t, E)) return rc;
+  return launch_elementwise(t, E);
+}
+int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (int rc = validate(t, E)) return rc;
+  if (t->op >= PDLB200_OP_CUMUSUMOVER && t->op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
+  if (t->op >= PDLB200_OP_SUMOVER && t->op <= PDLB200_OP_BXOROVER) return launch_reduce(t, E);
+  return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
+}
+int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (int rc = validate(t, E)) return rc;
+  if (t->op != PDLB200_OP_MATMULT) return E.fail(PDLB200_EINVAL, "%s is not matmult", pdlb200_op_name(t->op));
+  return launch_matmult(t, E);
+}
+int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (int rc = validate(t, E)) return rc;
+  const int op = t->op;
+  if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT) return launch_elementwise(t, E);
+  if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
+  if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_BXOROVER) return launch_reduce(t, E);
+  if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);
+  return E.fail(PDLB200_EINVAL, "pdlb200: op %d has no launcher", op);
+}
+
+// ---- device data store ---------------------------------------------------------
+struct pdlb200_buf {
+  void *dev;
+  size_t nbytes;
+  int device;
+  int dev_dirty;  // device copy newer than any host copy
+};
+
+int pdlb200_buf_new(size_t nbytes, pdlb200_buf **out, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (!out) return E.fail(PDLB200_EINVAL, "pdlb200_buf_new: NULL out");
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_buf_new: no CUDA device available");
+  pdlb200_buf *b = new pdlb200_buf{nullptr, nbytes, 0, 0};
+  cudaGetDevice(&b->device);
+  if (nbytes) {
+    // Stream-ordered pool: freed blocks are reused without returning to the driver, and there
+    // is no zero-fill (the reference's memset in pdl_allocdata is ~75% of its config-1 time).
+    cudaError_t e = cudaMallocAsync(&b->dev, nbytes, (cudaStream_t)0);
+    if (e != cudaSuccess) { delete b; return E.fail(PDLB200_ECUDA, "cudaMallocAsync(%zu): %s", nbytes, cudaGetErrorString(e)); }
+  }
+  *out = b;
+  return PDLB200_OK;
+}
+void pdlb200_buf_free(pdlb200_buf *b) {
+  if (!b) return;
+  if (b->dev) cudaFreeAsync(b->dev, (cudaStream_t)0);
+  delete b;
+}
+size_t pdlb200_buf_nbytes(const pdlb200_buf *b) { return b ? b->nbytes : 0; }
+void *pdlb200_buf_devptr(pdlb200_buf *b, int for_write) {
+  if (!b) return nullptr;
+  if (for_write) b->dev_dirty = 1;
+  return b->dev;
+}
+int pdlb200_buf_device_dirty(const pdlb200_buf *b) { return b ? b->dev_dirty : 0; }
+int pdlb200_buf_upload(pdlb200_buf *b, const void *host, size_t nbytes, void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (!b || nbytes > b->nbytes) return E.fail(PDLB200_EINVAL, "pdlb200_buf_upload: bad buffer or size");
+  if (nbytes) PDLB200_CUDA_OK(cudaMemcpyAsync(b->dev, host, nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), E);
+  b->dev_dirty = 0;
+  return PDLB200_OK;
+}
+int pdlb200_buf_download(pdlb200_buf *b, void *host, size_t nbytes, int force, void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (!b || nbytes > b->nbytes) return E.fail(PDLB200_EINVAL, "pdlb200_buf_download: bad buffer or size");
+  if (!b->dev_dirty && !force) return PDLB200_OK;
+  if (nbytes) PDLB200_CUDA_OK(cudaMemcpyAsync(host, b->dev, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), E);
+  PDLB200_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream), E);
+  b->dev_dirty = 0;
+  return PDLB200_OK;
+}
+
+void *pdlb200_host_alloc(size_t nbytes) {
+  if (probe_devices() <= 0) return nullptr;
+  void *p = nullptr;
+  if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pdlb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+int pdlb200_memcpy_h2d(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_memcpy_h2d: no CUDA device available");
+  PDLB200_CUDA_OK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream), E);
+  return PDLB200_OK;
+}
+int pdlb200_memcpy_d2h(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_memcpy_d2h: no CUDA device available");
+  PDLB200_CUDA_OK(cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), E);
+  return PDLB200_OK;
+}
+
+}  // extern "C"

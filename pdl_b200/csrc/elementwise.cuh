@@ -1,0 +1,181 @@
+// elementwise.cuh — the broadcast-loop walker kernel for PDL::Ops bodies.
+//
+// Replaces the two innermost `for`s of PDL_BROADCASTLOOP_START plus the odometer
+// of PDL_BROADCASTLOOP_END (lib/PDL/Core/pdl.h.PL:640-675,
+// lib/PDL/Core/pdlbroadcast.h:72-84) for the biop / bifunc / ufunc bodies of
+// lib/PDL/Ops.pd:104-265.  Roofline: HBM.  Algorithmic bytes per element:
+// sizeof(T) * (distinct inputs read + 1 output written); stride-0 (dummy)
+// operands cost nothing.
+//
+// Work unit = VEC = 16/sizeof(T) consecutive positions along collapsed dim 0
+// (one 128-bit register image per operand).  A thread owns UNROLL units per trip
+// of a grid-stride loop, issues all its loads first (UNROLL*NIN independent
+// 128-bit LDGs in flight), then computes and stores.  Operands that are not
+// unit-stride/16B-aligned along dim 0 (strided slices, reversed views, dummy
+// dims) are gathered element-wise into the same register image, so vaffine views
+// are read in place and never materialised.
+#pragma once
+#include "common.cuh"
+
+namespace pdlb200 {
+
+struct EwPlan {
+  char *ptr[3];                // operand base (offs applied), bytes; [NIN] is the output
+  int64_t st[3][MAXD];         // element strides per collapsed dim
+  int64_t dims[MAXD];
+  int64_t n_units;             // vpr * prod(dims[1..])
+  int64_t vpr;                 // vectors per row = ceil(dims[0]/VEC)
+  uint64_t bad[3];             // badvalue bits per operand
+  int nd;
+  int badnan[3];
+  int badchk[3];               // test this input for BAD (state flag for biop; always for bifunc/ufunc)
+  int vec[3];                  // 128-bit access allowed on full units
+};
+
+// Vector access moves VEC elements = VEC*sizeof(T) bytes (16 for same-type ops;
+// 8/4/2/1 for the narrow side of a convert).
+template <int BYTES> struct vec_word;
+template <> struct vec_word<16> { using type = uint4; };
+template <> struct vec_word<8>  { using type = uint2; };
+template <> struct vec_word<4>  { using type = uint32_t; };
+template <> struct vec_word<2>  { using type = uint16_t; };
+template <> struct vec_word<1>  { using type = uint8_t; };
+
+template <class T, int VEC>
+__device__ __forceinline__ void ew_load(Pack<T> &r, const char *base, int64_t off, int64_t st0, int vec_ok, int cnt) {
+  using W = typename vec_word<VEC * sizeof(T)>::type;
+  const T *p = reinterpret_cast<const T *>(base) + off;
+  if (vec_ok && cnt == VEC) {
+    *reinterpret_cast<W *>(&r) = *reinterpret_cast<const W *>(p);
+  } else if (st0 == 0) {
+    T v = *p;
+#pragma unroll
+    for (int k = 0; k < VEC; k++) r.e[k] = v;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; k++) r.e[k] = (k < cnt) ? p[k * st0] : T(0);
+  }
+}
+
+template <class T, int VEC>
+__device__ __forceinline__ void ew_store(const Pack<T> &r, char *base, int64_t off, int64_t st0, int vec_ok, int cnt) {
+  using W = typename vec_word<VEC * sizeof(T)>::type;
+  T *p = reinterpret_cast<T *>(base) + off;
+  if (vec_ok && cnt == VEC) {
+    *reinterpret_cast<W *>(p) = *reinterpret_cast<const W *>(&r);
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; k++) if (k < cnt) p[k * st0] = r.e[k];
+  }
+}
+
+// Op: struct with `template<class T> static __device__ T f(T a, T b)`.
+// TI = input element type, TO = output element type (differ only for convert).
+template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
+__global__ void __launch_bounds__(EW_THREADS)
+ew_kernel(const __grid_constant__ EwPlan p) {
+  constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const TI abad = from_bits<TI>(p.bad[0]);
+  const TI bbad = from_bits<TI>(p.bad[NIN > 1 ? 1 : 0]);
+  const TO cbad = from_bits<TO>(p.bad[NIN]);
+
+  for (int64_t u0 = tid; u0 < p.n_units; u0 += nthreads * UNROLL) {
+    // Pack<> is sized for 16 bytes of the WIDER type; with mixed widths (convert)
+    // the narrower side simply uses the first VEC lanes of its image.
+    Pack<TI> ra[UNROLL], rb[UNROLL];
+    int64_t oc[UNROLL];
+    int cnt[UNROLL];
+#pragma unroll
+    for (int j = 0; j < UNROLL; j++) {
+      const int64_t u = u0 + (int64_t)j * nthreads;
+      cnt[j] = 0;
+      if (u < p.n_units) {
+        int64_t row, v;
+        if (p.nd == 1) { row = 0; v = u; }
+        else if ((uint64_t)p.n_units <= 0xffffffffull) {
+          uint32_t r32 = (uint32_t)u / (uint32_t)p.vpr; row = r32; v = (uint32_t)u - r32 * (uint32_t)p.vpr;
+        } else { row = u / p.vpr; v = u - row * p.vpr; }
+        const int64_t i0 = v * VEC;
+        int64_t oa = i0 * p.st[0][0], ob = (NIN > 1) ? i0 * p.st[1][0] : 0, o = i0 * p.st[NIN][0];
+        for (int d = 1; d < p.nd; d++) {
+          int64_t q, i;
+          if (d == p.nd - 1) { i = row; q = 0; }
+          else if ((uint64_t)row <= 0xffffffffull && (uint64_t)p.dims[d] <= 0xffffffffull) {
+            uint32_t q32 = (uint32_t)row / (uint32_t)p.dims[d]; q = q32; i = (uint32_t)row - q32 * (uint32_t)p.dims[d];
+          } else { q = row / p.dims[d]; i = row - q * p.dims[d]; }
+          oa += i * p.st[0][d];
+          if (NIN > 1) ob += i * p.st[1][d];
+          o += i * p.st[NIN][d];
+          row = q;
+        }
+        const int64_t left = p.dims[0] - i0;
+        cnt[j] = left < VEC ? (int)left : VEC;
+        oc[j] = o;
+        ew_load<TI, VEC>(ra[j], p.ptr[0], oa, p.st[0][0], p.vec[0], cnt[j]);
+        if (NIN > 1) ew_load<TI, VEC>(rb[j], p.ptr[1], ob, p.st[1][0], p.vec[1], cnt[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNROLL; j++) {
+      if (cnt[j] > 0) {
+        Pack<TO> rc;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+          const TI a = ra[j].e[k];
+          const TI b = (NIN > 1) ? rb[j].e[k] : TI(0);
+          bool bad = false;
+          if constexpr (BAD) {
+            bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
+            if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
+          }
+          const TO r = Op::template f<TI, TO>(a, b);
+          rc.e[k] = bad ? cbad : r;
+        }
+        ew_store<TO, VEC>(rc, p.ptr[NIN], oc[j], p.st[NIN][0], p.vec[NIN], cnt[j]);
+      }
+    }
+  }
+}
+
+// host side: build the plan and launch (ew_plan.cu)
+int ew_build_plan(const pdlb200_trans *t, int nin, size_t in_size, size_t out_size,
+                  bool state_checked_bad, EwPlan *p, const Err &E);
+int ew_grid(int64_t n_units, int unroll, const void *kernel);
+
+template <class Op, class TI, class TO, int NIN>
+int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *name, const Err &E) {
+  EwPlan p;
+  int rc = ew_build_plan(t, NIN, sizeof(TI), sizeof(TO), state_checked_bad, &p, E);
+  if (rc) return rc;
+  if (p.n_units == 0) return PDLB200_OK;  // empty broadcast: the loop body never runs
+  constexpr int UNROLL = 4;
+  cudaStream_t s = (cudaStream_t)t->stream;
+  if (t->bvalflag) {
+    auto k = ew_kernel<Op, TI, TO, true, NIN, UNROLL>;
+    k<<<ew_grid(p.n_units, UNROLL, (const void *)k), EW_THREADS, 0, s>>>(p);
+  } else {
+    auto k = ew_kernel<Op, TI, TO, false, NIN, UNROLL>;
+    k<<<ew_grid(p.n_units, UNROLL, (const void *)k), EW_THREADS, 0, s>>>(p);
+  }
+  note_launch(name);
+  PDLB200_CUDA_OK(cudaGetLastError(), E);
+  return PDLB200_OK;
+}
+
+// dispatch a same-type op over the 11 device types; IND shares int64_t with LL.
+#define PDLB200_EW_CASES_INT(OP, NIN, SC, NAME) \
+  case PDLB200_SB:  return ew_launch_typed<OP, int8_t,   int8_t,   NIN>(t, SC, NAME, E); \
+  case PDLB200_B:   return ew_launch_typed<OP, uint8_t,  uint8_t,  NIN>(t, SC, NAME, E); \
+  case PDLB200_S:   return ew_launch_typed<OP, int16_t,  int16_t,  NIN>(t, SC, NAME, E); \
+  case PDLB200_US:  return ew_launch_typed<OP, uint16_t, uint16_t, NIN>(t, SC, NAME, E); \
+  case PDLB200_L:   return ew_launch_typed<OP, int32_t,  int32_t,  NIN>(t, SC, NAME, E); \
+  case PDLB200_UL:  return ew_launch_typed<OP, uint32_t, uint32_t, NIN>(t, SC, NAME, E); \
+  case PDLB200_IND: case PDLB200_LL: return ew_launch_typed<OP, int64_t, int64_t, NIN>(t, SC, NAME, E); \
+  case PDLB200_ULL: return ew_launch_typed<OP, uint64_t, uint64_t, NIN>(t, SC, NAME, E);
+#define PDLB200_EW_CASES_FLT(OP, NIN, SC, NAME) \
+  case PDLB200_F:   return ew_launch_typed<OP, float,  float,  NIN>(t, SC, NAME, E); \
+  case PDLB200_D:   return ew_launch_typed<OP, double, double, NIN>(t, SC, NAME, E);
+
+}  // namespace pdlb200

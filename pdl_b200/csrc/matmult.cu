@@ -1,0 +1,207 @@
+// matmult.cu — PDL::Primitive::matmult, a(t,h); b(w,t); [o]c(w,h)  (lib/PDL/Primitive.pd:191-264).
+//
+// c(w,h) = sum_t a(t,h) * b(w,t): in memory order (dim 0 fastest) that is the row-major
+// product C[h][w] = A[h][t] . B[t][w], each operand with arbitrary element strides
+// (sliced / transposed / dummy views are read in place) and optional broadcast (batch) dims.
+//
+// Two kernels:
+//  * mm_exact_kernel — every type, BAD-aware.  Shared-memory tiled SIMT; each output is
+//    accumulated strictly left-to-right over t with separate multiply and add (-fmad=false),
+//    i.e. the reference's own summation order (Primitive.pd:236-240), so results are bit-exact
+//    for integer types AND for float/double.  Bound: FP64/FP32 pipe at 2 instructions per MAC.
+//  * mm_dmma_kernel (matmult_dmma.cu) — double, no BAD: FP64 tensor-core tiles; fused multiply-add
+//    inside the MMA, so equal only within the stated tolerance (exact for exactly-representable inputs).
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+
+namespace pdlb200 {
+
+struct MmPlan {
+  const char *a, *b; char *c;      // bases with offs applied
+  int64_t T, H, W;                 // sizes of t, h, w
+  int64_t iat, iah, ibw, ibt, icw, ich;  // element strides
+  int64_t dims[MAXD];              // collapsed broadcast (batch) dims
+  int64_t sa[MAXD], sb[MAXD], sc[MAXD];
+  int64_t nbatch;
+  uint64_t abad, bbad, cbad;
+  int nd;
+  int abadnan, bbadnan, cbadnan;
+};
+
+int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E);  // matmult_dmma.cu
+
+constexpr int MM_BM = 64, MM_BN = 64, MM_BK = 16, MM_TM = 4, MM_TN = 4;
+
+template <class T> struct mm_acc { using type = T; };
+template <> struct mm_acc<int8_t>   { using type = uint32_t; };
+template <> struct mm_acc<uint8_t>  { using type = uint32_t; };
+template <> struct mm_acc<int16_t>  { using type = uint32_t; };
+template <> struct mm_acc<uint16_t> { using type = uint32_t; };
+template <> struct mm_acc<int32_t>  { using type = uint32_t; };
+template <> struct mm_acc<uint32_t> { using type = uint32_t; };
+template <> struct mm_acc<int64_t>  { using type = uint64_t; };
+template <> struct mm_acc<uint64_t> { using type = uint64_t; };
+
+template <class T, bool BAD>
+__global__ void __launch_bounds__(256)
+mm_exact_kernel(const __grid_constant__ MmPlan p) {
+  using A = typename mm_acc<T>::type;  // wrap-around accumulator; low bits == the reference's `cc += a*b` in T
+  constexpr int64_t TSIZ = 8 * sizeof(double) / sizeof(T);  // the reference's tile edge (Primitive.pd:212)
+  __shared__ T sA[MM_BK][MM_BM + 1];
+  __shared__ T sB[MM_BK][MM_BN + 1];
+  __shared__ unsigned char fA[BAD ? MM_BK : 1][BAD ? MM_BM + 1 : 1];  // BAD flags of the staged tiles
+  __shared__ unsigned char fB[BAD ? MM_BK : 1][BAD ? MM_BN + 1 : 1];
+
+  int64_t oa = 0, ob = 0, oc = 0;
+  {
+    int64_t row = blockIdx.z;
+    for (int d = 0; d < p.nd; d++) {
+      const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
+      const int64_t i = row - q * p.dims[d];
+      oa += i * p.sa[d]; ob += i * p.sb[d]; oc += i * p.sc[d];
+      row = q;
+    }
+  }
+  const T *Ap = reinterpret_cast<const T *>(p.a) + oa;
+  const T *Bp = reinterpret_cast<const T *>(p.b) + ob;
+  T *Cp = reinterpret_cast<T *>(p.c) + oc;
+  const T abad = from_bits<T>(p.abad), bbad = from_bits<T>(p.bbad), cbad = from_bits<T>(p.cbad);
+
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  const int64_t h0 = (int64_t)blockIdx.y * MM_BM, w0 = (int64_t)blockIdx.x * MM_BN;
+
+  A acc[MM_TM][MM_TN];
+  // BAD mode (Primitive.pd:227,235,241): 0 live; 1 stopped because cc itself tested BAD at a t-tile start
+  // (value kept); 2 stopped because a BAD a/b was met (c = c's badvalue).  Either way it stays stopped.
+  unsigned char frozen[MM_TM][MM_TN];
+#pragma unroll
+  for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+    for (int j = 0; j < MM_TN; j++) { acc[i][j] = A(0); frozen[i][j] = 0; }
+
+  for (int64_t t0 = 0; t0 < p.T; t0 += MM_BK) {
+    // stage A[h0..h0+BM) x [t0..t0+BK)  and  B[t0..t0+BK) x [w0..w0+BN); threads run along t for A
+    // and along w for B, the unit-stride dims of PDL's default layout
+    for (int e = threadIdx.x; e < MM_BM * MM_BK; e += 256) {
+      const int k = e % MM_BK, m = e / MM_BK;
+      const int64_t h = h0 + m, tt_ = t0 + k;
+      T v = T(0); unsigned char f = 0;
+      if (h < p.H && tt_ < p.T) {
+        v = Ap[tt_ * p.iat + h * p.iah];
+        if (BAD) f = is_bad(v, abad, p.abadnan != 0);
+      }
+      sA[k][m] = v;
+      if (BAD) fA[k][m] = f;
+    }
+    for (int e = threadIdx.x; e < MM_BK * MM_BN; e += 256) {
+      const int n = e % MM_BN, k = e / MM_BN;
+      const int64_t w = w0 + n, tt_ = t0 + k;
+      T v = T(0); unsigned char f = 0;
+      if (w < p.W && tt_ < p.T) {
+        v = Bp[w * p.ibw + tt_ * p.ibt];
+        if (BAD) f = is_bad(v, bbad, p.bbadnan != 0);
+      }
+      sB[k][n] = v;
+      if (BAD) fB[k][n] = f;
+    }
+    __syncthreads();
+    const int kmax = (p.T - t0) < MM_BK ? (int)(p.T - t0) : MM_BK;
+#pragma unroll
+    for (int k = 0; k < MM_BK; k++) {
+      if (k < kmax) {
+        T av[MM_TM], bv[MM_TN];
+        unsigned char af[MM_TM], bf[MM_TN];
+#pragma unroll
+        for (int i = 0; i < MM_TM; i++) { av[i] = sA[k][ty * MM_TM + i]; if (BAD) af[i] = fA[k][ty * MM_TM + i]; }
+#pragma unroll
+        for (int j = 0; j < MM_TN; j++) { bv[j] = sB[k][tx * MM_TN + j]; if (BAD) bf[j] = fB[k][tx * MM_TN + j]; }
+#pragma unroll
+        for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+          for (int j = 0; j < MM_TN; j++) {
+            if (BAD) {
+              // the reference re-tests cc against c's badvalue at every t-tile start (Primitive.pd:227)
+              if (((t0 + k) % TSIZ) == 0 && !frozen[i][j] && is_bad((T)acc[i][j], cbad, p.cbadnan != 0)) frozen[i][j] = 1;
+              if (!frozen[i][j] && (af[i] | bf[j])) frozen[i][j] = 2;
+              if (frozen[i][j]) continue;
+            }
+            if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
+            else acc[i][j] = acc[i][j] + av[i] * bv[j];  // two roundings, as on the reference's x86-64 build
+          }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+    for (int j = 0; j < MM_TN; j++) {
+      const int64_t h = h0 + ty * MM_TM + i, w = w0 + tx * MM_TN + j;
+      if (h < p.H && w < p.W) {
+        T out = (T)acc[i][j];
+        if (BAD && frozen[i][j] == 2) out = cbad;
+        Cp[w * p.icw + h * p.ich] = out;
+      }
+    }
+}
+
+template <class T>
+static int mm_launch(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
+  dim3 grid((unsigned)((p.W + MM_BN - 1) / MM_BN), (unsigned)((p.H + MM_BM - 1) / MM_BM), (unsigned)p.nbatch);
+  cudaStream_t s = (cudaStream_t)t->stream;
+  if (t->bvalflag) mm_exact_kernel<T, true><<<grid, 256, 0, s>>>(p);
+  else mm_exact_kernel<T, false><<<grid, 256, 0, s>>>(p);
+  note_launch("matmult_exact");
+  PDLB200_CUDA_OK(cudaGetLastError(), E);
+  return PDLB200_OK;
+}
+
+int launch_matmult(const pdlb200_trans *t, const Err &E) {
+  if (t->npdls != 3) return E.fail(PDLB200_EINVAL, "matmult: expected 3 parameters, got %d", t->npdls);
+  MmPlan p;
+  memset(&p, 0, sizeof p);
+  p.T = t->ind[0]; p.H = t->ind[1]; p.W = t->ind[2];
+  if (p.T < 0 || p.H < 0 || p.W < 0) return E.fail(PDLB200_EINVAL, "matmult: negative dim size");
+  p.iat = t->rinc[0]; p.iah = t->rinc[1]; p.ibw = t->rinc[2]; p.ibt = t->rinc[3]; p.icw = t->rinc[4]; p.ich = t->rinc[5];
+  Collapsed c;
+  collapse_dims(t, &c);
+  if (c.nd > MAXD) return E.fail(PDLB200_EUNSUPPORTED, "matmult: %d non-mergeable broadcast dims exceed %d", c.nd, MAXD);
+  p.nd = c.nd; p.nbatch = c.total;
+  for (int d = 0; d < c.nd; d++) { p.dims[d] = c.dims[d]; p.sa[d] = c.st[0][d]; p.sb[d] = c.st[1][d]; p.sc[d] = c.st[2][d]; }
+  if (p.nbatch == 0 || p.H == 0 || p.W == 0) return PDLB200_OK;
+  if (p.nbatch > 65535) return E.fail(PDLB200_EUNSUPPORTED, "matmult: %lld broadcast positions exceed the 65535 grid limit", (long long)p.nbatch);
+  const size_t sz = pdlb200_type_size(t->datatype);
+  for (int k = 0; k < 3; k++)
+    if (!t->pdls[k].data) return E.fail(PDLB200_EINVAL, "matmult: parameter %d got NULL data", k);
+  p.a = (const char *)t->pdls[0].data + t->pdls[0].offs * (int64_t)sz;
+  p.b = (const char *)t->pdls[1].data + t->pdls[1].offs * (int64_t)sz;
+  p.c = (char *)t->pdls[2].data + t->pdls[2].offs * (int64_t)sz;
+  p.abad = t->pdls[0].badval; p.bbad = t->pdls[1].badval; p.cbad = t->pdls[2].badval;
+  p.abadnan = (t->pdls[0].flags & PDLB200_PAR_BADNAN) != 0;
+  p.bbadnan = (t->pdls[1].flags & PDLB200_PAR_BADNAN) != 0;
+  p.cbadnan = (t->pdls[2].flags & PDLB200_PAR_BADNAN) != 0;
+
+  const char *force = getenv("PDLB200_MATMULT");  // "exact" | "dmma" (default: dmma when eligible)
+  const bool want_exact = force && !strcmp(force, "exact");
+  if (t->datatype == PDLB200_D && !t->bvalflag && !want_exact) {
+    int rc = launch_matmult_dmma(t, p, E);
+    if (rc != PDLB200_EUNSUPPORTED) return rc;  // shape not eligible -> exact kernel
+  }
+  switch (t->datatype) {
+    case PDLB200_SB:  return mm_launch<int8_t>(t, p, E);
+    case PDLB200_B:   return mm_launch<uint8_t>(t, p, E);
+    case PDLB200_S:   return mm_launch<int16_t>(t, p, E);
+    case PDLB200_US:  return mm_launch<uint16_t>(t, p, E);
+    case PDLB200_L:   return mm_launch<int32_t>(t, p, E);
+    case PDLB200_UL:  return mm_launch<uint32_t>(t, p, E);
+    case PDLB200_IND: case PDLB200_LL: return mm_launch<int64_t>(t, p, E);
+    case PDLB200_ULL: return mm_launch<uint64_t>(t, p, E);
+    case PDLB200_F:   return mm_launch<float>(t, p, E);
+    case PDLB200_D:   return mm_launch<double>(t, p, E);
+    default: break;
+  }
+  return E.fail(PDLB200_EUNSUPPORTED, "matmult: type %d is not on the device path", t->datatype);
+}
+
+}  // namespace pdlb200

@@ -1,0 +1,31 @@
+// reduce_minmax.cu — minimum maximum minimum_ind maximum_ind (lib/PDL/Ufunc.pd:446-500).
+#include "reduce.cuh"
+namespace pdlb200 {
+template <class T> struct MinV { using R = RMinMax<T, T, false, false>; };
+#define MM_CASES(ISMAX, WANT, NAME) \
+  case PDLB200_SB:  return mm<int8_t,   ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_B:   return mm<uint8_t,  ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_S:   return mm<int16_t,  ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_US:  return mm<uint16_t, ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_L:   return mm<int32_t,  ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_UL:  return mm<uint32_t, ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_IND: case PDLB200_LL: return mm<int64_t, ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_ULL: return mm<uint64_t, ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_F:   return mm<float,    ISMAX, WANT>(t, NAME, E); \
+  case PDLB200_D:   return mm<double,   ISMAX, WANT>(t, NAME, E);
+template <class T, bool ISMAX, bool WANT>
+static int mm(const pdlb200_trans *t, const char *name, const Err &E) {
+  if constexpr (WANT) return rd_launch_typed<RMinMax<T, int64_t, ISMAX, true>, T, int64_t>(t, name, E);
+  else return rd_launch_typed<RMinMax<T, T, ISMAX, false>, T, T>(t, name, E);
+}
+int reduce_minmax_family(const pdlb200_trans *t, const Err &E) {
+  switch (t->op) {
+    case PDLB200_OP_MINIMUM:     switch (t->datatype) { MM_CASES(false, false, "reduce_minimum")     default: break; } break;
+    case PDLB200_OP_MAXIMUM:     switch (t->datatype) { MM_CASES(true,  false, "reduce_maximum")     default: break; } break;
+    case PDLB200_OP_MINIMUM_IND: switch (t->datatype) { MM_CASES(false, true,  "reduce_minimum_ind") default: break; } break;
+    case PDLB200_OP_MAXIMUM_IND: switch (t->datatype) { MM_CASES(true,  true,  "reduce_maximum_ind") default: break; } break;
+    default: break;
+  }
+  return E.fail(PDLB200_EUNSUPPORTED, "%s: type %d is not on the device path", pdlb200_op_name(t->op), t->datatype);
+}
+}  // namespace pdlb200

@@ -1,0 +1,85 @@
+// reduce_plan.cu — host planner for the Ufunc reductions: collapse the broadcast
+// dims, pick the cooperation width (thread / warp / CTA per row) and, when rows are
+// too few to fill the GPU, the number of chunks each row is cut into.
+#include <cstdlib>
+#include <cstring>
+#include "reduce.cuh"
+
+namespace pdlb200 {
+
+int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_t acc_size,
+                  RdPlan *p, RdLaunch *l, const Err &E) {
+  if (t->npdls != 2)
+    return E.fail(PDLB200_EINVAL, "%s: expected 2 parameters, got %d", pdlb200_op_name(t->op), t->npdls);
+  if (t->ind[0] < 0) return E.fail(PDLB200_EINVAL, "%s: size of dim n is %lld", pdlb200_op_name(t->op), (long long)t->ind[0]);
+  Collapsed c;
+  collapse_dims(t, &c);
+  if (c.nd > MAXD)
+    return E.fail(PDLB200_EUNSUPPORTED, "%s: %d non-mergeable broadcast dims exceed the device walker's %d",
+                  pdlb200_op_name(t->op), c.nd, MAXD);
+  memset(p, 0, sizeof *p);
+  p->n = t->ind[0];
+  p->inc_n = t->rinc[0];
+  p->nrows = c.total;
+  p->nd = c.nd;
+  for (int d = 0; d < c.nd; d++) { p->dims[d] = c.dims[d]; p->sa[d] = c.st[0][d]; p->sb[d] = c.st[1][d]; }
+  if (c.total > 0 && (!t->pdls[1].data || (p->n > 0 && !t->pdls[0].data)))
+    return E.fail(PDLB200_EINVAL, "%s: parameter got NULL data", pdlb200_op_name(t->op));
+  p->a = (const char *)t->pdls[0].data + t->pdls[0].offs * (int64_t)in_size;
+  p->b = (char *)t->pdls[1].data + t->pdls[1].offs * (int64_t)out_size;
+  p->abad = t->pdls[0].badval; p->bbad = t->pdls[1].badval;
+  p->abadnan = (t->pdls[0].flags & PDLB200_PAR_BADNAN) != 0;
+  p->badmode = t->bvalflag != 0;
+  p->chunk = p->n; p->nchunks = 1;
+  if (p->nrows == 0) return PDLB200_OK;
+
+  const int sms = sm_count();
+  const int64_t n = p->n;
+  // "column" reduction: the reduced dim is strided but broadcast dim 0 is unit-stride in a,
+  // so one thread per row makes every warp-wide load a contiguous run.
+  const bool column = (p->inc_n != 1 || n <= 1) && (p->sa[0] == 1 || p->sa[0] == -1) && p->dims[0] >= 32;
+  int mode;
+  if (column) mode = 0;
+  else if ((int64_t)n * (int64_t)in_size >= 32768) mode = 2;
+  else if (n >= 64) mode = 1;
+  else mode = 0;
+  if (const char *e = getenv("PDLB200_REDUCE_MODE")) { int m = atoi(e); if (m >= 0 && m <= 2) mode = m; }
+
+  const int64_t rows_per_cta = mode == 0 ? RD_THREADS : mode == 1 ? RD_THREADS / 32 : 1;
+  int64_t ctas = (p->nrows + rows_per_cta - 1) / rows_per_cta;
+  const int64_t target = (int64_t)sms * 8;
+  // too few row-CTAs: cut n into chunks (>= 16K elements each so the partial traffic stays negligible)
+  const int64_t min_chunk = mode == 0 ? 256 : 16384;
+  if (ctas < target / 2 && n >= 2 * min_chunk) {
+    int64_t want = (target + ctas - 1) / ctas;
+    int64_t maxc = n / min_chunk;
+    if (want > maxc) want = maxc;
+    if (want > 65535) want = 65535;
+    if (want > 1) {
+      int64_t chunk = (n + want - 1) / want;
+      chunk = (chunk + 4095) / 4096 * 4096;   // keeps 16-byte alignment of chunk starts for every type
+      p->chunk = chunk;
+      p->nchunks = (int)((n + chunk - 1) / chunk);
+    }
+  }
+  if (const char *e = getenv("PDLB200_REDUCE_CHUNKS")) {
+    int want = atoi(e);
+    if (want >= 1 && want <= 65535 && n > 0) {
+      int64_t chunk = (n + want - 1) / want; chunk = (chunk + 4095) / 4096 * 4096;
+      p->chunk = chunk; p->nchunks = (int)((n + chunk - 1) / chunk);
+    }
+  }
+  if (p->nchunks > 1) {
+    p->partial = (char *)scratch((size_t)p->nrows * p->nchunks * acc_size, (cudaStream_t)t->stream);
+    if (!p->partial) return E.fail(PDLB200_ECUDA, "%s: cannot allocate %zu bytes of reduction scratch",
+                                   pdlb200_op_name(t->op), (size_t)p->nrows * p->nchunks * acc_size);
+  }
+  int64_t gx = ctas;
+  const int64_t cap = (target + p->nchunks - 1) / p->nchunks;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  l->mode = mode;
+  l->grid = dim3((unsigned)gx, (unsigned)p->nchunks, 1);
+  return PDLB200_OK;
+}
+
+}  // namespace pdlb200

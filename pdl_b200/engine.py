@@ -1,0 +1,139 @@
+"""Execution engine behind pdl_b200.PDL: where ndarray bytes live and who runs a
+transformation's readdata.
+
+The product has exactly ONE engine, `CudaEngine`, which talks to libpdlb200.so
+through the C-ABI in include/pdlb200.h.  There is no CPU engine in this package
+and no fallback: constructing a CudaEngine without the built library or without
+a GPU raises.  (tests/ plug the C oracle in through the same small interface to
+check the CUDA results; that lives under oracle/, never here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _abi
+
+
+class PDLError(RuntimeError):
+    """What the reference reports through barf / pdl_error (lib/PDL/Core/pdlutil.c:507-529)."""
+
+
+class Store:
+    """One device allocation (the reference's pdl.datasv / pdl.data, pdlapi.c:172-209)."""
+
+    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "__weakref__")
+
+    def __init__(self, engine, handle, ptr, nbytes, keep=None):
+        self.engine, self.handle, self.ptr, self.nbytes, self._keep = engine, handle, ptr, nbytes, keep
+
+
+class Engine:
+    """Interface a PDL object needs from its engine."""
+
+    name = "abstract"
+
+    def alloc(self, nbytes: int) -> Store:
+        raise NotImplementedError
+
+    def upload(self, store: Store, host: np.ndarray) -> None:
+        raise NotImplementedError
+
+    def download(self, store: Store, nbytes: int) -> np.ndarray:
+        raise NotImplementedError
+
+    def readdata(self, trans: _abi.Trans) -> None:
+        raise NotImplementedError
+
+    def sync(self) -> None:
+        pass
+
+
+class CudaEngine(Engine):
+    """libpdlb200.so on one B200.  One process drives one GPU (torchrun sets LOCAL_RANK)."""
+
+    name = "cuda"
+
+    def __init__(self, device: int | None = None):
+        self.lib = _abi.load()  # raises LibraryMissing if the extension is not built
+        if self.lib.pdlb200_abi_version() != 1:
+            raise PDLError("libpdlb200.so ABI version mismatch")
+        n = self.lib.pdlb200_device_count()
+        if n <= 0:
+            raise PDLError("pdl_b200: no CUDA device is visible and there is no CPU fallback")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) % n
+        self.device = device
+        self._err = C.create_string_buffer(512)
+        self._check(self.lib.pdlb200_set_device(device, self._err, 512))
+        self.stream = None  # legacy default stream: ordered with torch's default stream
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise PDLError(self._err.value.decode("utf-8", "replace"))
+
+    def alloc(self, nbytes: int) -> Store:
+        h = C.c_void_p()
+        self._check(self.lib.pdlb200_buf_new(nbytes, C.byref(h), self._err, 512))
+        ptr = self.lib.pdlb200_buf_devptr(h, 0) or 0
+        st = Store(self, h.value, ptr, nbytes)
+        weakref.finalize(st, self.lib.pdlb200_buf_free, h.value)
+        return st
+
+    def wrap(self, ptr: int, nbytes: int, keep) -> Store:
+        """Adopt foreign device memory (e.g. a torch tensor kept alive by `keep`)."""
+        return Store(self, None, ptr, nbytes, keep)
+
+    def upload(self, store: Store, host: np.ndarray) -> None:
+        host = np.ascontiguousarray(host)
+        if host.nbytes > store.nbytes:
+            raise PDLError("upload larger than the allocation")
+        if host.nbytes:
+            self._check(self.lib.pdlb200_memcpy_h2d(store.ptr, host.ctypes.data, host.nbytes, self.stream, self._err, 512))
+            self.sync()  # pageable source: make the call's completion explicit
+
+    def upload_ptr(self, store: Store, host_ptr: int, nbytes: int, offset: int = 0) -> None:
+        """Asynchronous H2D from (pinned) host memory into store[offset:offset+nbytes]."""
+        self._check(self.lib.pdlb200_memcpy_h2d(store.ptr + offset, host_ptr, nbytes, self.stream, self._err, 512))
+
+    def download(self, store: Store, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        if nbytes:
+            self._check(self.lib.pdlb200_memcpy_d2h(out.ctypes.data, store.ptr, nbytes, self.stream, self._err, 512))
+        self.sync()
+        return out
+
+    def download_ptr(self, store: Store, host_ptr: int, nbytes: int) -> None:
+        self._check(self.lib.pdlb200_memcpy_d2h(host_ptr, store.ptr, nbytes, self.stream, self._err, 512))
+
+    def readdata(self, trans: _abi.Trans) -> None:
+        trans.stream = self.stream
+        self._check(self.lib.pdlb200_readdata(C.byref(trans), self._err, 512))
+
+    def sync(self) -> None:
+        self._check(self.lib.pdlb200_sync(self.stream, self._err, 512))
+
+    def launch_count(self) -> int:
+        return int(self.lib.pdlb200_launch_count())
+
+    def last_kernel(self) -> str:
+        return (self.lib.pdlb200_last_kernel() or b"").decode()
+
+
+_default: Engine | None = None
+
+
+def default_engine() -> Engine:
+    """The process-wide CudaEngine, created on first use.  Raises without GPU/library."""
+    global _default
+    if _default is None:
+        _default = CudaEngine()
+    return _default
+
+
+def set_default_engine(e: Engine | None) -> None:
+    global _default
+    _default = e

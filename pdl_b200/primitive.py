@@ -1,0 +1,30 @@
+"""PDL::Primitive::matmult on the device path (lib/PDL/Primitive.pd:191-264)."""
+from __future__ import annotations
+
+from .core import PDL
+from .engine import PDLError
+from .trans import run_op, as_pdl
+
+
+def matmult(x, y, c=None) -> PDL:
+    """The Perl wrapper PDL::matmult restated (Primitive.pd:197-209): promote to >= 2 dims,
+    scalar shortcut through `*`, dim check with the reference's message, then _matmult_int."""
+    x = as_pdl(x)
+    y = as_pdl(y, x.engine)
+    while x.getndims() < 2:
+        x = x.dummy(-1)
+    while y.getndims() < 2:
+        y = y.dummy(-1)
+    if (x.dim(0) == 1 and x.dim(1) == 1) or (y.dim(0) == 1 and y.dim(1) == 1):
+        r = x * y
+        if c is not None and not c.isnull():
+            c.assign(r)
+            return c
+        return r
+    if y.dim(1) != x.dim(0):
+        raise PDLError("Dim mismatch in matmult of [%dx%d] x [%dx%d]: %d != %d" %
+                       (x.dim(0), x.dim(1), y.dim(0), y.dim(1), x.dim(0), y.dim(1)))
+    return run_op("matmult", [x, y], [c])[0]
+
+
+__all__ = ["matmult"]

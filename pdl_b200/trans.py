@@ -1,0 +1,367 @@
+"""pdl_run_<op> for the device path: everything the reference does between the XS stub
+and readdata, restated on PDL metadata, ending in ONE pdlb200_readdata call.
+
+Reference call stack being mirrored:
+  type selection     pdl__transtype_select        lib/PDL/Core/pdlapi.c:1182-1236
+  output typing      pdl__set_output_type_badvalue lib/PDL/Core/pdlapi.c:1240-1260
+  input conversion   pdl__type_convert            lib/PDL/Core/pdlapi.c:1262-1311 (on device: OP_CONVERT)
+  bvalflag/badflag   pdl_make_trans_mutual        lib/PDL/Core/pdlapi.c:760-770,806-808
+  named dims         pdl_dim_checks               lib/PDL/Core/pdlbroadcast.c:211-273
+  broadcast dims     pdl_initbroadcaststruct      lib/PDL/Core/pdlbroadcast.c:340-488
+  output creation    pdl_broadcast_create_parameter lib/PDL/Core/pdlbroadcast.c:490-523
+  real-dim incs      pdl_redodims_default         lib/PDL/Core/pdlapi.c:858-864
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi, types as T
+from .core import PDL, _default_incs
+from .engine import Engine, PDLError, default_engine
+
+# parameter flags (subset of PDL_PARAM_*, lib/PDL/Core/pdl.h.PL:412-425)
+TYPED, TPLUS = 1, 2
+
+
+@dataclass
+class Par:
+    name: str
+    realdims: tuple = ()        # named dims, e.g. ('n',) or ('t','h')
+    out: bool = False
+    typed: int | None = None    # forced type (double, indx, long for int+)
+    tplus: bool = False         # `int+`: max(typed, trans type)
+
+
+@dataclass
+class OpSpec:
+    name: str
+    pars: list
+    gentypes: tuple             # GenericTypes, in declaration order (last = fallback)
+    kind: str                   # biop | bifunc | ufunc | reduce | matmult | convert
+    inplace: tuple = ()         # parameter names that may run in place
+    opid: int = field(init=False)
+
+    def __post_init__(self):
+        self.opid = _abi.OPS[self.name]
+
+
+_A, _R, _I = T.ALL, T.REAL, T.INTEGER
+# Ops.pd:8-9,321,332: [@$C, @$F] with D last so that non-float input falls back to double
+_CF = T.COMPLEX + T.FLOATING
+_F = T.FLOATING
+
+
+def _bi(name, gentypes, kind="biop"):
+    return OpSpec(name, [Par("a"), Par("b"), Par("c", out=True)], gentypes, kind, inplace=("a",))
+
+
+def _un(name, gentypes):
+    return OpSpec(name, [Par("a"), Par("b", out=True)], gentypes, "ufunc", inplace=("a",))
+
+
+def _rd(name, gentypes, typed=None, tplus=False):
+    return OpSpec(name, [Par("a", ("n",)), Par("b", out=True, typed=typed, tplus=tplus)], gentypes, "reduce")
+
+
+SPECS = {s.name: s for s in [
+    # biop, lib/PDL/Ops.pd:288-313
+    _bi("plus", _A), _bi("mult", _A), _bi("minus", _A), _bi("divide", _A),
+    _bi("gt", _R), _bi("lt", _R), _bi("le", _R), _bi("ge", _R), _bi("eq", _A), _bi("ne", _A),
+    _bi("shiftleft", _I), _bi("shiftright", _I), _bi("or2", _I), _bi("and2", _I), _bi("xor", _I),
+    # bifunc, lib/PDL/Ops.pd:321-324
+    _bi("power", _CF, "bifunc"), _bi("atan2", _F, "bifunc"), _bi("modulo", _R, "bifunc"),
+    _bi("spaceship", _R, "bifunc"),
+    # ufunc etc., lib/PDL/Ops.pd:327-397,491-503
+    _un("bitnot", _I), _un("sqrt", _A), _un("sin", _A), _un("cos", _A), _un("not", _R),
+    _un("exp", _CF), _un("log", _CF), _un("log10", _A), _un("_rabs", _R),
+    OpSpec("assgn", [Par("a"), Par("b", out=True)], _A, "ufunc"),
+    OpSpec("abs2", [Par("a"), Par("b", out=True)], _A, "ufunc"),
+    # reductions, lib/PDL/Ufunc.pd:88-118,143-187,413-500
+    _rd("sumover", _A, T.L, True), _rd("prodover", _A, T.L, True),
+    _rd("dsumover", _R, T.D), _rd("dprodover", _R, T.D),
+    _rd("average", _R, T.L, True), _rd("daverage", _R, T.D),
+    _rd("minimum", _R), _rd("maximum", _R),
+    _rd("minimum_ind", _R, T.IND), _rd("maximum_ind", _R, T.IND),
+    _rd("andover", _A), _rd("orover", _A), _rd("zcover", _A), _rd("xorover", _A),
+    _rd("bandover", _I), _rd("borover", _I), _rd("bxorover", _I),
+    # matmult, lib/PDL/Primitive.pd:191-195
+    OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
+]}
+
+
+# ---- scalars -> ndarrays (pdl_SvPDLV + pdl_scalar, lib/PDL/Core/pdlcore.c:64-78) -----------
+
+def as_pdl(x, engine: Engine | None = None) -> PDL:
+    if isinstance(x, PDL):
+        return x
+    engine = engine or default_engine()
+    if isinstance(x, (bool, int, float, np.integer, np.floating)):
+        t = T.scalar_type(x)
+        return PDL.from_numpy(np.array(x, dtype=T.NP_DTYPE[t]), t, engine)
+    if isinstance(x, (list, tuple, np.ndarray)):
+        from .core import pdl
+        return pdl(x, engine=engine)
+    raise PDLError(f"Error - tried to use an unknown data structure as a PDL: {type(x).__name__}")
+
+
+# ---- type selection ---------------------------------------------------------------------------
+
+def transtype_select(spec: OpSpec, pdls: list) -> int:
+    """pdl__transtype_select (pdlapi.c:1182-1236): outputs that already exist decide first,
+    then the highest input type that is in GenericTypes; types above the list's last entry
+    (or none available) fall back to the LAST GenericTypes entry."""
+    avail = set(spec.gentypes)
+    last = spec.gentypes[-1]
+    if spec.gentypes[0] == last:
+        return last
+    nparents = sum(1 for p in spec.pars if not p.out)
+    retval, use_last = -1, False
+    for i in range(len(spec.pars) - 1, -1, -1):
+        par, p = spec.pars[i], pdls[i]
+        if p is not None and not p.isnull() and par.typed is None:
+            new = p.datatype
+            ok = new in avail
+            if not ok and new > last:
+                use_last = True
+            if ok and retval < new:
+                retval = new
+        if i == nparents and retval != -1:
+            return retval
+    if use_last or retval == -1 or retval not in avail:
+        retval = last
+    return retval
+
+
+def par_type(par: Par, transtype: int) -> int:
+    """PDL_TYPE_ADJUST_FROM_TRANS (pdlapi.c:1174-1181)."""
+    if par.typed is not None:
+        return max(par.typed, transtype) if par.tplus else par.typed
+    return transtype
+
+
+def convert_type(p: PDL, datatype: int) -> PDL:
+    """converttype on the device (lib/PDL/Core/pdlconv.c:45-126): BAD maps to the TARGET
+    type's default badvalue; the result has no per-ndarray badvalue."""
+    if not T.is_device_type(datatype) or not T.is_device_type(p.datatype):
+        raise PDLError(f"type {T.NAMES[datatype]} has no device representation")
+    out = PDL.empty(datatype, p.dims, p.engine)
+    out.badflag = p.badflag
+    _launch(SPECS_CONVERT, p.datatype, [p, out], _broadcast([p, out], [0, 0], [False, False], "converttype"),
+            {}, bval=p.badflag)
+    return out
+
+
+SPECS_CONVERT = OpSpec.__new__(OpSpec)
+SPECS_CONVERT.name, SPECS_CONVERT.kind, SPECS_CONVERT.opid = "converttype", "convert", _abi.OPS["converttype"]
+SPECS_CONVERT.pars = [Par("a"), Par("b", out=True)]
+SPECS_CONVERT.gentypes, SPECS_CONVERT.inplace = T.ALL, ()
+
+
+# ---- broadcast struct ---------------------------------------------------------------------------
+
+@dataclass
+class Broadcast:
+    dims: list          # broadcast.dims (ndims >= 2: nobl=2, pdlapi.c:839)
+    nimpl: int
+    incs: list          # incs[d][p]
+
+
+def _broadcast(pdls: list, realdims: list, creating: list, opname: str) -> Broadcast:
+    """pdl_initbroadcaststruct + pdl_broadcast_dim_checks for implicit broadcast dims."""
+    np_ = len(pdls)
+    nimpl = 0
+    for j, p in enumerate(pdls):
+        if creating[j]:
+            continue
+        nimpl = max(nimpl, p.ndims - realdims[j])
+    ndims = max(nimpl, 2)
+    dims = [1] * ndims
+    incs = [[0] * np_ for _ in range(ndims)]
+    for nth in range(nimpl):
+        for j, p in enumerate(pdls):
+            if creating[j]:
+                continue
+            k = nth + realdims[j]
+            if k >= p.ndims:
+                continue
+            cur = p.dims[k]
+            if cur != 1:
+                if dims[nth] != 1:
+                    if dims[nth] != cur:
+                        raise PDLError(
+                            f"PDL: PDL::{opname}(...): Parameter '{j}':\n"
+                            f"Mismatched implicit broadcast dimension {nth}: size {dims[nth]} vs. {cur}")
+                else:
+                    dims[nth] = cur
+                incs[nth][j] = p.dimincs[k]
+    return Broadcast(dims, nimpl, incs)
+
+
+def _check_output_dims(p: PDL, realdims: int, bc: Broadcast, opname: str, pname: str) -> None:
+    """An existing output cannot be broadcast over (pdlbroadcast.c:286-306)."""
+    for nth in range(bc.nimpl):
+        k = nth + realdims
+        if k >= p.ndims:
+            if bc.dims[nth] != 1:
+                raise PDLError(f"PDL::{opname}: implicit dim {nth} size {bc.dims[nth]}, "
+                               f"can't broadcast over output ndarray with size > 1")
+            continue
+        if p.dims[k] == 1 and bc.dims[nth] != 1:
+            raise PDLError(f"PDL::{opname}: implicit dim {nth} size {bc.dims[nth]}, but dim has size 1")
+        if p.dims[k] != 1 and p.dimincs[k] == 0:
+            raise PDLError(f"PDL::{opname}: implicit dim {nth} size {bc.dims[nth]}, but dim is dummy")
+
+
+# ---- the descriptor ---------------------------------------------------------------------------
+
+def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> None:
+    if len(bc.dims) > _abi.MAXDIMS:
+        raise PDLError(f"PDL::{spec.name}: more than {_abi.MAXDIMS} broadcast dims")
+    tr = _abi.Trans()
+    tr.op, tr.datatype, tr.bvalflag = spec.opid, transtype, int(bool(bval))
+    tr.npdls, tr.ndims = len(pdls), len(bc.dims)
+    for d, n in enumerate(bc.dims):
+        tr.dims[d] = n
+        for j in range(len(pdls)):
+            tr.incs[d * len(pdls) + j] = bc.incs[d][j]
+    for k, v in enumerate(named.get("ind", ())):
+        tr.ind[k] = v
+    for k, v in enumerate(named.get("rinc", ())):
+        tr.rinc[k] = v
+    for j, p in enumerate(pdls):
+        par = tr.pdls[j]
+        par.data = p.store.ptr if p.store is not None else None
+        par.offs = p.offs
+        par.type = p.datatype
+        par.badval = p.badvalue_bits()
+        par.flags = (_abi.PAR_BADFLAG if p.badflag else 0) | (_abi.PAR_BADNAN if p.badvalue_isnan() else 0)
+    pdls[0].engine.readdata(tr)
+
+
+def _real_inc(p: PDL, j: int) -> int:
+    # pdl_redodims_default (pdlapi.c:858-864)
+    return 0 if (p.ndims <= j or p.dims[j] <= 1) else p.dimincs[j]
+
+
+def run_op(name: str, inputs: list, outputs: list | None = None) -> list:
+    """pdl_run_<name>(inputs..., outputs...).  `outputs` entries may be None (null ndarray:
+    created with the broadcast dims).  Returns the output ndarrays."""
+    spec = SPECS[name]
+    in_pars = [p for p in spec.pars if not p.out]
+    out_pars = [p for p in spec.pars if p.out]
+    if len(inputs) != len(in_pars):
+        raise PDLError(f"PDL::{name}: expected {len(in_pars)} inputs")
+    outputs = list(outputs) if outputs is not None else [None] * len(out_pars)
+    engine = next((x.engine for x in list(inputs) + outputs if isinstance(x, PDL)), None) or default_engine()
+    ins = [as_pdl(x, engine) for x in inputs]
+    for x in ins:
+        if x.isnull():
+            raise PDLError(f"PDL::{name}: input parameter is null")
+    outs = [None if (o is None or o.isnull()) else o for o in outputs]
+
+    all_pdls = ins + outs
+    transtype = transtype_select(spec, all_pdls)
+    if not T.is_device_type(transtype):
+        raise PDLError(f"PDL::{name}: type {T.NAMES[transtype]} has no device representation "
+                       "(long double / complex are outside the device type matrix)")
+    # inputs to the type the loop is instantiated for (converttypei -> device convert kernel)
+    ins = [x if x.datatype == par_type(par, transtype) else convert_type(x, par_type(par, transtype))
+           for x, par in zip(ins, in_pars)]
+    bval = any(x.badflag for x in ins)
+
+    # named dims (pdl_dim_checks): inputs define them; size-1 stretches; missing dims promote to 1
+    ind: dict = {}
+    for x, par in zip(ins, in_pars):
+        for j, dn in enumerate(par.realdims):
+            sz = x.dims[j] if j < x.ndims else 1
+            if dn not in ind or ind[dn] == 1:
+                ind[dn] = sz
+            elif sz != ind[dn] and sz != 1:
+                raise PDLError(f"PDL::{name}: Parameter '{par.name}' index '{dn}' size {ind[dn]}, "
+                               f"but ndarray dim has size {sz}")
+    for o, par in zip(outs, out_pars):
+        if o is None:
+            continue
+        for j, dn in enumerate(par.realdims):
+            sz = o.dims[j] if j < o.ndims else 1
+            if dn in ind and sz != ind[dn]:
+                raise PDLError(f"PDL::{name}: Parameter '{par.name}' index '{dn}' size {ind[dn]}, "
+                               f"but ndarray dim has size {sz}")
+
+    realdims = [len(p.realdims) for p in spec.pars]
+    creating = [False] * len(ins) + [o is None for o in outs]
+    placeholder = [x for x in ins] + [o if o is not None else ins[0] for o in outs]
+    bc = _broadcast(placeholder, realdims, creating, name)
+
+    final_outs, temps = [], []
+    for k, (o, par) in enumerate(zip(outs, out_pars)):
+        want = par_type(par, transtype)
+        if o is None:
+            dims = [ind[dn] for dn in par.realdims] + bc.dims[:bc.nimpl]
+            o = PDL.empty(want, dims, engine)
+            target = o
+        else:
+            _check_output_dims(o, len(par.realdims), bc, name, par.name)
+            # an existing output of another type: compute in the op type, convert back afterwards
+            target = o if o.datatype == want else PDL.empty(want, o.dims, engine)
+            if target is not o:
+                temps.append((target, o))
+        final_outs.append(o)
+        j = len(ins) + k
+        rd = len(par.realdims)
+        for nth in range(bc.nimpl):
+            kk = nth + rd
+            bc.incs[nth][j] = target.dimincs[kk] if (kk < target.ndims and target.dims[kk] != 1) else 0
+        placeholder[j] = target
+
+    # pdl_make_trans_mutual: any BAD input -> every output carries the badflag (pdlapi.c:806-808)
+    if bval:
+        for o in placeholder[len(ins):]:
+            o.badflag = True
+
+    named = {}
+    if spec.kind == "reduce":
+        a = placeholder[0]
+        named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0)]}
+        # minimum/maximum and the and/or..over family set the output badflag themselves when a row has
+        # no good element (Ufunc.pd:463-464,177); without BAD inputs that can only be n == 0.
+        if ind["n"] == 0 and name in ("minimum", "maximum", "minimum_ind", "maximum_ind"):
+            for o in placeholder[len(ins):]:
+                o.badflag = True
+    elif spec.kind == "matmult":
+        a, b, c = placeholder
+        named = {"ind": [ind["t"], ind["h"], ind["w"]],
+                 "rinc": [_real_inc(a, 0), _real_inc(a, 1), _real_inc(b, 0), _real_inc(b, 1),
+                          _real_inc(c, 0), _real_inc(c, 1)]}
+    _launch(spec, transtype, placeholder, bc, named, bval)
+
+    for target, o in temps:
+        conv = convert_type(target, o.datatype)
+        run_op("assgn", [conv], [o])
+        o.badflag = o.badflag or target.badflag
+    return final_outs
+
+
+# ---- the three generator shapes of Ops.pd ----------------------------------------------------
+
+def run_biop(name: str, a, b, c=None, swap: int = 0) -> PDL:
+    """XS PDL::<name>(a,b,[c],swap): swap a/b, then PDL_XS_INPLACE (lib/PDL/Ops.pd:108-114,
+    lib/PDL/Core/pdlperl.h:61-71)."""
+    engine = next((x.engine for x in (a, b, c) if isinstance(x, PDL)), None)
+    a, b = as_pdl(a, engine), as_pdl(b, engine)
+    if swap:
+        a, b = b, a
+    if c is None and a.is_inplace():
+        a._inplace = False
+        c = a
+    return run_op(name, [a, b], [c])[0]
+
+
+def run_ufunc(name: str, a, b=None) -> PDL:
+    a = as_pdl(a)
+    if b is None and a.is_inplace():
+        a._inplace = False
+        b = a
+    return run_op(name, [a], [b])[0]

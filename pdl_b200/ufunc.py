@@ -1,0 +1,48 @@
+"""PDL::Ufunc surface on the device path (lib/PDL/Ufunc.pd): the `Xover` reductions along
+dim 0 and the whole-array wrappers `sum max ...` = `$x->flat->Xover` (Ufunc.pd:618-663)."""
+from __future__ import annotations
+
+from .trans import run_op, as_pdl
+
+_REDUCERS = ["sumover", "prodover", "dsumover", "dprodover", "average", "daverage",
+             "minimum", "maximum", "minimum_ind", "maximum_ind",
+             "andover", "orover", "zcover", "xorover", "bandover", "borover", "bxorover"]
+
+
+def _mk(name):
+    def f(a, b=None):
+        return run_op(name, [as_pdl(a)], [b])[0]
+    f.__name__ = name
+    f.__doc__ = f"PDL::{name}(a(n); [o]b()) — lib/PDL/Ufunc.pd"
+    return f
+
+
+for _n in _REDUCERS:
+    globals()[_n] = _mk(_n)
+
+# synonyms (Ufunc.pd:431,470)
+avgover = globals()["average"]
+davgover = globals()["daverage"]
+minover = globals()["minimum"]
+maxover = globals()["maximum"]
+minover_ind = globals()["minimum_ind"]
+maxover_ind = globals()["maximum_ind"]
+
+_WHOLE = {"sum": "sumover", "prod": "prodover", "avg": "average", "dsum": "dsumover",
+          "dprod": "dprodover", "davg": "daverage", "min": "minimum", "max": "maximum",
+          "zcheck": "zcover", "and_": "andover", "or_": "orover", "band": "bandover",
+          "bor": "borover", "xorall": "xorover", "bxor": "bxorover"}
+
+
+def _mk_whole(name, over):
+    def f(a):
+        return globals()[over](as_pdl(a).flat())
+    f.__name__ = name
+    f.__doc__ = f"PDL::{name.rstrip('_')}: $x->flat->{over} (lib/PDL/Ufunc.pd:660)"
+    return f
+
+
+for _n, _o in _WHOLE.items():
+    globals()[_n] = _mk_whole(_n, _o)
+
+__all__ = _REDUCERS + list(_WHOLE) + ["avgover", "davgover", "minover", "maxover", "minover_ind", "maxover_ind"]

@@ -1,0 +1,106 @@
+"""Replay helpers shared by the golden / parity tests: rebuild a recorded input on a given
+engine, apply its view chain, make the recorded call through pdl_b200's operator surface."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+import pdl_b200 as P
+from pdl_b200 import types as T, ufunc, ops
+from pdl_b200.engine import PDLError
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+TYPE_ID = {n: i for i, n in enumerate(T.NAMES)}
+
+
+def load_cases(fname):
+    return json.loads((GOLDEN / fname).read_text())["cases"]
+
+
+def build_input(spec, engine):
+    if "scalar" in spec:
+        v = spec["scalar"]
+        return int(v) if spec.get("is_int") else float(v)
+    t = TYPE_ID[spec["type"]]
+    raw = np.frombuffer(bytes.fromhex(spec["hex"]), dtype=T.NP_DTYPE[t])
+    p = P.PDL.from_numpy(raw.reshape(list(reversed(spec["dims"]))), t, engine)
+    p.badflag = bool(spec["badflag"])
+    bv = np.frombuffer(bytes.fromhex(spec["badvalue_hex"]), dtype=T.NP_DTYPE[t])[0]
+    default = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+    if bv.tobytes() != default.tobytes():
+        p.set_badvalue(float(bv) if t in (T.F, T.D) else int(bv))
+    for v in spec.get("views", []):
+        p = getattr(p, v[0])(*v[1:])
+    return p
+
+
+def run_call(call, args):
+    kind = call["kind"]
+    if kind == "biop":
+        a, b = args
+        if call.get("inplace"):
+            a = a.copy().inplace()
+        return P.run_biop(call["op"], a, b, None, call.get("swap", 0))
+    if kind == "ufunc":
+        op = {"abs": "_rabs"}.get(call["op"], call["op"])
+        return P.run_ufunc(op, args[0])
+    if kind == "reduce":
+        return getattr(ufunc, call["op"])(args[0])
+    if kind == "whole":
+        return getattr(ufunc, call["op"])(args[0])
+    if kind == "matmult":
+        return P.matmult(args[0], args[1])
+    if kind == "convert":
+        return args[0].convert(TYPE_ID[call["to"]])
+    raise ValueError(kind)
+
+
+def ulp_diff(got: np.ndarray, want: np.ndarray) -> int:
+    """Largest distance in units-in-the-last-place between two float arrays of equal dtype;
+    identical NaN-ness and infinities are required."""
+    assert got.dtype == want.dtype
+    it = np.int32 if got.dtype == np.float32 else np.int64
+    g, w = got.reshape(-1), want.reshape(-1)
+    nan_g, nan_w = np.isnan(g), np.isnan(w)
+    if not np.array_equal(nan_g, nan_w):
+        return 1 << 62
+    gi, wi = g.view(it).astype(np.int64), w.view(it).astype(np.int64)
+    # map the sign-magnitude float ordering onto a monotone integer line
+    mn = np.int64(np.iinfo(it).min)
+    gi = np.where(gi < 0, mn - gi, gi)
+    wi = np.where(wi < 0, mn - wi, wi)
+    d = np.abs(gi - wi)
+    d[nan_g] = 0
+    return int(d.max()) if d.size else 0
+
+
+def check_case(case, engine):
+    """Replay one recorded case on `engine`; assert type, dims, badflag and values."""
+    args = [build_input(s, engine) for s in case["inputs"]]
+    if "error" in case:
+        try:
+            run_call(case["call"], args)
+        except PDLError as e:
+            want = case["error"]
+            key = "Mismatched implicit broadcast dimension" if "Mismatched" in want else "Dim mismatch in matmult"
+            assert key in str(e), (str(e), want)
+            if "Dim mismatch" in want:
+                assert str(e).strip() == want.strip()
+            return
+        raise AssertionError(f"{case['name']}: reference raised {case['error']!r}, we did not")
+    out = run_call(case["call"], args)
+    want = case["output"]
+    assert out.type == want["type"], (case["name"], out.type, want["type"])
+    assert out.dims == want["dims"], (case["name"], out.dims, want["dims"])
+    assert int(out.badflag) == want["badflag"], (case["name"], "badflag", out.badflag, want["badflag"])
+    dt = T.NP_DTYPE[out.datatype]
+    got = out.to_numpy().reshape(-1)
+    exp = np.frombuffer(bytes.fromhex(want["hex"]), dtype=dt)
+    tol = case.get("tol_ulp")
+    if tol and dt.kind == "f":
+        d = ulp_diff(got, exp)
+        assert d <= tol, (case["name"], f"{d} ulp > {tol}", got, exp)
+    else:
+        assert got.tobytes() == exp.tobytes(), (case["name"], got, exp)
