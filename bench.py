@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the PDL broadcast-loop hot path on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+  sumover / average / minimum along dim 0 of a [16384, 65536] float ndarray with 1% BAD.
+One STEP = those three reductions over the whole 4 GiB ndarray (3 x 2^30 elements).
+  value     : elements/sec, whole job, inputs resident in HBM (device data store).
+  e2e       : same metric through the host-buffer path — pinned host ndarray -> H2D -> the
+              three reductions -> D2H of the three result ndarrays, all inside the timed region.
+  roofline  : slowest of the three kernels; achieved = algorithmic bytes / CUDA-event time.
+  N > 1     : one process per GPU; the ndarray is partitioned along its outermost broadcast
+              dim (rows), every rank reduces its own [16384, 65536] block, no data-path
+              collective -> weak scaling.  `extra.cfg5` additionally times
+              the full-array sum/max of the same resident 2^30-element shard per GPU plus the
+              NCCL allreduce that collapses the sharded dim (BASELINE.json configs[4]).
+  --impl reference : the UNMODIFIED reference (PDL built into oracle/_ref) on the host cores,
+              all threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_DIM = 16384          # reduced dim (dim 0), contiguous
+ROWS = 65536           # broadcast dim per GPU
+WORKLOAD = "cfg2: sumover+average+minimum over dim 0 of float[16384,65536], 1% BAD"
+OPS = ("sumover", "average", "minimum")
+SEED = 0x5EED
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic input: counter hash of the flat index; identical in torch (device
+# generation), numpy (oracle sample) and PDL (oracle/ref_bench.pl)
+# ---------------------------------------------------------------------------------------------
+def _hash_numpy(idx):
+    import numpy as np
+    z = idx.astype(np.uint64) + np.uint64(SEED)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def sample_numpy(row0: int, rows: int):
+    """float32 [rows, N_DIM] block (numpy C order == PDL dims [N_DIM, rows]) + BAD as -FLT_MAX."""
+    import numpy as np
+    idx = (np.arange(rows * N_DIM, dtype=np.uint64) + np.uint64(row0 * N_DIM))
+    z = _hash_numpy(idx)
+    vals = ((z >> np.uint64(11)) % np.uint64(17)).astype(np.float32) - np.float32(8)
+    bad = ((z >> np.uint64(40)) % np.uint64(100)) == 0
+    vals[bad] = -np.finfo(np.float32).max
+    return vals.reshape(rows, N_DIM)
+
+
+def generate_device(torch, row0: int, rows: int, device):
+    """Same block generated on the device in 2048-row chunks (int64 wrap-around arithmetic)."""
+    out = torch.empty((rows, N_DIM), dtype=torch.float32, device=device)
+    m1 = 0xBF58476D1CE4E5B9 - (1 << 64)
+    m2 = 0x94D049BB133111EB - (1 << 64)
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    step = 2048
+    for r in range(0, rows, step):
+        rr = min(step, rows - r)
+        idx = torch.arange(rr * N_DIM, dtype=torch.int64, device=device) + (row0 + r) * N_DIM
+        z = idx + SEED
+        z = (z ^ lsr(z, 30)) * m1
+        z = (z ^ lsr(z, 27)) * m2
+        z = z ^ lsr(z, 31)
+        vals = (lsr(z, 11) % 17).to(torch.float32) - 8.0
+        bad = (lsr(z, 40) % 100) == 0
+        vals[bad] = -torch.finfo(torch.float32).max
+        out[r:r + rr] = vals.view(rr, N_DIM)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def _clock_sampler(stop, samples):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    dev = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", dev, f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            parts = [p.strip() for p in r.stdout.strip().split(",")]
+            if len(parts) >= 6:
+                samples.append(parts)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = [int(s[0]) for s in samples if s[0].isdigit()]
+    mx = [int(s[1]) for s in samples if s[1].isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for k, n in enumerate(names) if any(s[2 + k] == "Active" for s in samples)]
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons, "samples": len(samples)}
+
+
+def _peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _ref_cmd(rows, steps, warmup, threads):
+    ref = ROOT / "oracle" / "_ref" / "blib"
+    return ["perl", f"-I{ref / 'lib'}", f"-I{ref / 'arch'}", str(ROOT / "oracle" / "ref_bench.pl"),
+            "--n", str(N_DIM), "--rows", str(rows), "--steps", str(steps), "--warmup", str(warmup),
+            "--threads", str(threads)]
+
+
+def _have_ref():
+    return (ROOT / "oracle" / "_ref" / "blib" / "arch" / "auto" / "PDL" / "Ufunc" / "Ufunc.so").exists()
+
+
+def run_reference_sample(rows, steps, warmup, threads):
+    r = subprocess.run(_ref_cmd(rows, steps, warmup, threads), capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0:
+        raise RuntimeError("reference run failed: " + r.stderr[-400:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def run_port_sample(rows, steps, warmup):
+    """The C restatement (oracle/pdl_oracle.c), single thread, on the same sample."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pdl_b200 as P
+    from pdl_b200 import types as T, ufunc
+    from oracle_engine import OracleEngine
+    e = OracleEngine()
+    a = P.PDL.from_numpy(sample_numpy(0, rows), T.F, e).set_badflag(True)
+    tot = 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for op in OPS:
+            getattr(ufunc, op)(a)
+        if it >= warmup:
+            tot += time.perf_counter() - t0
+    return {"ms_per_step": 1000 * tot / steps, "elements_per_sec": 3 * rows * N_DIM * steps / tot}
+
+
+# ---------------------------------------------------------------------------------------------
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    rows = 4096  # bounded sample: 4096 of 65536 rows = 256 MiB; reference time scales linearly in rows
+    if _have_ref():
+        res = run_reference_sample(rows, args.steps, args.warmup, cores)
+        kind, threads = "reference", int(res.get("autopthread_actual") or 0) or 1
+        detail = f"PDL {res['pdl_version']} autopthread target {cores}, actual {res.get('autopthread_actual')}"
+    else:
+        res = run_port_sample(rows, args.steps, args.warmup)
+        kind, threads, detail = "port", 1, "oracle/pdl_oracle.c (oracle/_ref not present)"
+    v = res["elements_per_sec"]
+    sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step; {detail}"
+    line = {
+        "impl": "reference", "metric": "elements/sec", "value": v, "unit": "elements/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"] * (ROWS / rows),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "elements/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main_ours(args):
+    import numpy as np
+    import torch
+    import pdl_b200 as P
+    from pdl_b200 import types as T, ufunc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    eng = P.CudaEngine(local)
+    P.set_default_engine(eng)
+
+    # ---- resident input: this rank's block of rows [rank*ROWS, (rank+1)*ROWS) ----
+    dev_in = generate_device(torch, rank * ROWS, ROWS, device)
+    torch.cuda.synchronize()
+    a = P.PDL(eng, eng.wrap(dev_in.data_ptr(), dev_in.numel() * 4, dev_in), T.F, [N_DIM, ROWS]).set_badflag(True)
+    outs = {op: P.PDL.empty(T.F, [ROWS], eng) for op in OPS}
+    for o in outs.values():
+        o.badflag = True
+
+    def step():
+        for op in OPS:
+            P.run_op(op, [a], [outs[op]])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region (device-resident): K steps, CUDA events on the launch stream ----
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=_clock_sampler, args=(stop, samples), daemon=True)
+    th.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    launches = eng.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+
+    # per-kernel times (same region repeated per op so each op's launches are bracketed alone)
+    per_op_ms = {}
+    for op in OPS:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            P.run_op(op, [a], [outs[op]])
+        e1.record()
+        torch.cuda.synchronize()
+        per_op_ms[op] = e0.elapsed_time(e1) / args.steps
+    stop.set()
+    th.join(timeout=2)
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    elems_step = 3 * N_DIM * ROWS * world
+    value = elems_step / (ms_step / 1e3)
+
+    peak, peak_src = _peak_hbm()
+    bytes_op = N_DIM * ROWS * 4 + ROWS * 4                      # 4 295 229 440 B per op
+    per_op = {op: {"ms": per_op_ms[op], "gbs": bytes_op / per_op_ms[op] / 1e6,
+                   "frac": bytes_op / per_op_ms[op] / 1e6 / peak,
+                   "elements_per_sec": N_DIM * ROWS / (per_op_ms[op] / 1e3)} for op in OPS}
+    dom = max(OPS, key=lambda o: per_op_ms[o])
+    roofline = {"bound": "hbm", "kernel": f"reduce_{dom} (reduce_rows_kernel)", "achieved": per_op[dom]["gbs"],
+                "peak": peak, "unit": "GB/s", "frac": per_op[dom]["frac"], "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_op}
+    prof = ROOT / "profiles" / "traffic.json"
+    if prof.exists():
+        try:
+            roofline["traffic"] = json.loads(prof.read_text()).get(f"reduce_{dom}")
+        except Exception:
+            pass
+
+    # ---- verify a slice of the results against the oracle (checker only, outside timing) ----
+    verified = None
+    if rank == 0:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        from oracle_engine import OracleEngine
+        oe = OracleEngine()
+        chk = 64
+        host = sample_numpy(rank * ROWS, chk)
+        pa = P.PDL.from_numpy(host, T.F, oe).set_badflag(True)
+        verified = True
+        for op in OPS:
+            want = getattr(ufunc, op)(pa).to_numpy()
+            got = outs[op].slice(f"0:{chk - 1}").to_numpy()
+            verified = verified and got.tobytes() == want.tobytes()
+
+    # ---- e2e: pinned host ndarray -> H2D -> 3 reductions -> D2H, per step ----
+    e2e_steps = max(1, min(args.steps, 5))
+    nbytes_in = N_DIM * ROWS * 4
+    host_in = torch.empty((ROWS, N_DIM), dtype=torch.float32, pin_memory=True)
+    host_in.copy_(dev_in)
+    host_out = torch.empty((3, ROWS), dtype=torch.float32, pin_memory=True)
+    stage = torch.empty((ROWS, N_DIM), dtype=torch.float32, device=device)
+    sa = P.PDL(eng, eng.wrap(stage.data_ptr(), nbytes_in, stage), T.F, [N_DIM, ROWS]).set_badflag(True)
+    e2e_outs = {op: P.PDL.empty(T.F, [ROWS], eng) for op in OPS}
+    copy_s, comp_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    SLABS = 16
+    rows_slab = ROWS // SLABS
+    slab_views = [(sa.slice(f":,{s * rows_slab}:{(s + 1) * rows_slab - 1}"),
+                   {op: e2e_outs[op].slice(f"{s * rows_slab}:{(s + 1) * rows_slab - 1}") for op in OPS})
+                  for s in range(SLABS)]
+    evs = [torch.cuda.Event() for _ in range(SLABS)]
+
+    def e2e_step():
+        # upload slab s on the copy stream while slab s-1 is being reduced on the compute stream
+        for s in range(SLABS):
+            off = s * rows_slab * N_DIM * 4
+            eng.stream = copy_s.cuda_stream
+            eng.upload_ptr(sa.store, host_in.data_ptr() + off, rows_slab * N_DIM * 4, off)
+            evs[s].record(copy_s)
+            comp_s.wait_event(evs[s])
+            eng.stream = comp_s.cuda_stream
+            view, o = slab_views[s]
+            for op in OPS:
+                P.run_op(op, [view], [o[op]])
+        for k, op in enumerate(OPS):
+            eng.download_ptr(e2e_outs[op].store, host_out.data_ptr() + k * ROWS * 4, ROWS * 4)
+        comp_s.synchronize()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    eng.stream = None
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = elems_step * e2e_steps / float(t.item())
+    e2e_ok = bool(np.array_equal(host_out[0].numpy().view(np.uint32), outs["sumover"].to_numpy().view(np.uint32)))
+
+    # ---- cfg5 extra: full-array sum / max of the resident shard + allreduce over the sharded dim ----
+    flat = a.reshape_view([N_DIM * ROWS])
+    part = torch.zeros(4, dtype=torch.float32, device=device)
+    psum = P.PDL(eng, eng.wrap(part.data_ptr(), 4, part), T.F, [])
+    pmax = P.PDL(eng, eng.wrap(part.data_ptr() + 4, 4, part), T.F, [])
+    psum.badflag = pmax.badflag = True
+
+    def cfg5():
+        P.run_op("sumover", [flat], [psum])
+        P.run_op("maximum", [flat], [pmax])
+        if dist is not None:
+            dist.all_reduce(part[0:1], op=dist.ReduceOp.SUM)
+            dist.all_reduce(part[1:2], op=dist.ReduceOp.MAX)
+
+    for _ in range(3):
+        cfg5()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cfg5()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cfg5_ms = float(t.item()) / args.steps
+    cfg5_extra = {"workload": f"cfg5: sum+max of float[2^30] per GPU x {world} GPUs" + (" + NCCL allreduce" if world > 1 else ""),
+                  "ms_per_step": cfg5_ms, "elements_per_sec": 2 * N_DIM * ROWS * world / (cfg5_ms / 1e3),
+                  "gbs_per_gpu": 2 * nbytes_in / cfg5_ms / 1e6, "frac_per_gpu": 2 * nbytes_in / cfg5_ms / 1e6 / peak,
+                  "sum": float(part[0].item()), "max": float(part[1].item())}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N == 1 only; bounded sample) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rows = 2048
+        sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step, 2 timed steps"
+        try:
+            if _have_ref():
+                r1 = run_reference_sample(rows, 2, 1, cores)
+                r0 = run_reference_sample(rows, 2, 1, 0)
+                cpu_baseline = {"value": r1["elements_per_sec"], "unit": "elements/s",
+                                "cores": int(r1.get("autopthread_actual") or 0) or 1, "kind": "reference",
+                                "sample": sample + f"; PDL {r1['pdl_version']} with autopthread ({r1.get('autopthread_actual')} threads)",
+                                "no_pthread": {"value": r0["elements_per_sec"], "cores": 1},
+                                "host_cores": cores}
+            else:
+                r = run_port_sample(rows, 2, 1)
+                cpu_baseline = {"value": r["elements_per_sec"], "unit": "elements/s", "cores": 1, "kind": "port",
+                                "sample": sample + "; oracle/pdl_oracle.c single thread", "host_cores": cores}
+        except Exception as ex:  # the baseline is reported, never required for the GPU numbers
+            cpu_baseline = {"value": None, "unit": "elements/s", "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+    line = {
+        "metric": "elements/sec", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "elements_per_step_per_gpu": 3 * N_DIM * ROWS,
+                   "partition": "rows (outermost broadcast dim) across ranks, no collective",
+                   "l2": "inputs (4 GiB per GPU) larger than L2", "timer": "cuda events, max over ranks"},
+        "roofline": roofline, "per_op": per_op,
+        "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 3 * ROWS * 4,
+                "steps": e2e_steps, "slabs": SLABS, "matches_resident_result": e2e_ok},
+        "gpu_launches": int(launches), "clocks": _clocks_summary(samples), "verified_vs_oracle": verified,
+        "cpu_baseline": cpu_baseline, "extra": {"cfg5": cfg5_extra},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import argparse
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -37,14 +38,27 @@ def _stale(target: Path, deps) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(src: Path, seen=None) -> set:
+    """Transitive closure of the quoted #includes of one source file."""
+    seen = set() if seen is None else seen
+    for inc in _INC.findall(src.read_text()):
+        f = (src.parent / inc).resolve()
+        if f.exists() and f not in seen:
+            seen.add(f)
+            _deps(f, seen)
+    return seen
+
+
 def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
-    headers = sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "pdlb200.h"]
     sources = sorted(CSRC.glob("*.cu"))
     todo = []
     for src in sources:
         obj = OBJ / (src.stem + ".o")
-        if force or _stale(obj, [src] + headers):
+        if force or _stale(obj, [src, *_deps(src)]):
             todo.append((src, obj))
 
     def compile_one(pair):

@@ -50,6 +50,30 @@ template <class T> __device__ __forceinline__ bool is_bad(T v, T badval, bool ba
   return badnan ? t_isnan(v) : (v == badval);
 }
 
+// NaN results the way the reference's x86-64 SSE code produces them (IEEE 754 leaves the bits
+// open; the GPU would return its canonical 0x7fffffff): a NaN operand is propagated, first
+// operand first, with the quiet bit set; an invalid operation (inf-inf, 0*inf, 0/0, sqrt(-1))
+// yields the x86 "default NaN", which is NEGATIVE quiet NaN.
+template <class T> __device__ __forceinline__ T quiet_nan(T v) {
+  if constexpr (sizeof(T) == 4) return __uint_as_float(__float_as_uint(v) | 0x00400000u);
+  else return __longlong_as_double(__double_as_longlong(v) | 0x0008000000000000ll);
+}
+template <class T> __device__ __forceinline__ T x86_default_nan() {
+  if constexpr (sizeof(T) == 4) return __uint_as_float(0xffc00000u);
+  else return __longlong_as_double((long long)0xfff8000000000000ull);
+}
+template <class T> __device__ __forceinline__ T x86_nan2(T a, T b, T r) {
+  if (r == r) return r;
+  if (a != a) return quiet_nan(a);
+  if (b != b) return quiet_nan(b);
+  return x86_default_nan<T>();
+}
+template <class T> __device__ __forceinline__ T x86_nan1(T a, T r) {
+  if (r == r) return r;
+  if (a != a) return quiet_nan(a);
+  return x86_default_nan<T>();
+}
+
 // 16-byte register image of VEC consecutive elements
 template <class T> union alignas(16) Pack {
   uint4 q;

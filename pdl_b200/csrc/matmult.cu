@@ -13,23 +13,10 @@
 //    inside the MMA, so equal only within the stated tolerance (exact for exactly-representable inputs).
 #include <cstdlib>
 #include <cstring>
-#include "common.cuh"
+#include "matmult.cuh"
 
 namespace pdlb200 {
 
-struct MmPlan {
-  const char *a, *b; char *c;      // bases with offs applied
-  int64_t T, H, W;                 // sizes of t, h, w
-  int64_t iat, iah, ibw, ibt, icw, ich;  // element strides
-  int64_t dims[MAXD];              // collapsed broadcast (batch) dims
-  int64_t sa[MAXD], sb[MAXD], sc[MAXD];
-  int64_t nbatch;
-  uint64_t abad, bbad, cbad;
-  int nd;
-  int abadnan, bbadnan, cbadnan;
-};
-
-int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E);  // matmult_dmma.cu
 
 constexpr int MM_BM = 64, MM_BN = 64, MM_BK = 16, MM_TM = 4, MM_TN = 4;
 
@@ -127,7 +114,10 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
               if (frozen[i][j]) continue;
             }
             if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
-            else acc[i][j] = acc[i][j] + av[i] * bv[j];  // two roundings, as on the reference's x86-64 build
+            else {  // two roundings (and x86 NaN rules), as on the reference's x86-64 build
+              const T m = x86_nan2(av[i], bv[j], av[i] * bv[j]);
+              acc[i][j] = x86_nan2(acc[i][j], m, acc[i][j] + m);
+            }
           }
       }
     }

@@ -1,0 +1,198 @@
+// matmult_dmma.cu — double-precision matmult on the FP64 tensor cores (DMMA).
+//
+// lib/PDL/Primitive.pd:191-264 for double, no BAD values, standard layout (t unit-stride in a,
+// w unit-stride in b): C[h][w] = sum_t A[h][t] * B[t][w].  tcgen05.mma has no f64 kind, so the
+// FP64 tensor path on sm_100a is mma.sync (SASS: DMMA).  Roofline: FP64 tensor peak;
+// 2*T*H*W flop, minimum traffic 8*(H*T + T*W + H*W) bytes.
+//
+// CTA tile 128x128, BK = 16, 256 threads = 8 warps (2 x 4), warp tile 64x32, 4-stage
+// cp.async (LDGSTS) ring.  Shared-memory rows are padded (A: 20 doubles, B: 132 doubles) so
+// that the 64-bit fragment loads of a half-warp hit 16 distinct banks.
+// The MMA adds with fused multiply-add, so results equal the reference's separate
+// multiply/add only within tolerance (bit-exact when every product and partial sum is exactly
+// representable; tests/test_gpu_parity.py pins both).
+#include <cstdlib>
+#include <cstring>
+#include "matmult.cuh"
+
+namespace pdlb200 {
+
+constexpr int DM_BM = 128, DM_BN = 128, DM_BK = 16, DM_STAGES = 4;
+constexpr int DM_LDA = DM_BK + 4;    // 20 doubles: rows 160 B apart (16B-aligned, conflict-free)
+constexpr int DM_LDB = DM_BN + 4;    // 132 doubles
+constexpr int DM_A_STAGE = DM_BM * DM_LDA;   // doubles
+constexpr int DM_B_STAGE = DM_BK * DM_LDB;
+constexpr size_t DM_SMEM = (size_t)DM_STAGES * (DM_A_STAGE + DM_B_STAGE) * sizeof(double);
+
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem, int bytes_valid, bool wide) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  if (wide) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(bytes_valid));
+  else      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(s), "l"(gmem), "r"(bytes_valid));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+// D(8x8) += A(8x4) * B(4x8).  lane: g = lane>>2, t = lane&3.  a = A[g][t], b = B[t][g], c{0,1} = C[g][2t+{0,1}]
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ALIGNED16: every row start of A, B (and the k/w offsets used) is 16-byte aligned -> 16-byte LDGSTS
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(256, 1)
+mm_dmma_kernel(const __grid_constant__ MmPlan p) {
+  extern __shared__ __align__(16) double smem[];
+  double *sA = smem;
+  double *sB = smem + DM_STAGES * DM_A_STAGE;
+
+  int64_t oa = 0, ob = 0, oc = 0;
+  {
+    int64_t row = blockIdx.z;
+    for (int d = 0; d < p.nd; d++) {
+      const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
+      const int64_t i = row - q * p.dims[d];
+      oa += i * p.sa[d]; ob += i * p.sb[d]; oc += i * p.sc[d];
+      row = q;
+    }
+  }
+  const double *A = reinterpret_cast<const double *>(p.a) + oa;
+  const double *B = reinterpret_cast<const double *>(p.b) + ob;
+  double *C = reinterpret_cast<double *>(p.c) + oc;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;         // 2 x 4 warps
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t h0 = (int64_t)blockIdx.y * DM_BM, w0 = (int64_t)blockIdx.x * DM_BN;
+  const int KT = (int)((p.T + DM_BK - 1) / DM_BK);
+
+  auto load_tile = [&](int kt, int slot) {
+    const int64_t k0 = (int64_t)kt * DM_BK;
+    double *dA = sA + slot * DM_A_STAGE;
+    double *dB = sB + slot * DM_B_STAGE;
+    if (ALIGNED16) {
+      // A: 128 rows x 8 chunks of 2 doubles; B: 16 rows x 64 chunks
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int c = tid + i * 256;
+        const int r = c >> 3, kc = (c & 7) * 2;
+        const int64_t h = h0 + r, k = k0 + kc;
+        int valid = 0;
+        if (h < p.H && k < p.T) valid = (p.T - k >= 2) ? 16 : 8;
+        const double *src = valid ? (A + h * p.iah + k) : A;
+        cp_async(dA + r * DM_LDA + kc, src, valid, true);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int c = tid + i * 256;
+        const int r = c >> 6, wc = (c & 63) * 2;
+        const int64_t k = k0 + r, w = w0 + wc;
+        int valid = 0;
+        if (k < p.T && w < p.W) valid = (p.W - w >= 2) ? 16 : 8;
+        const double *src = valid ? (B + k * p.ibt + w) : B;
+        cp_async(dB + r * DM_LDB + wc, src, valid, true);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int c = tid + i * 256;
+        const int r = c >> 4, kc = c & 15;
+        const int64_t h = h0 + r, k = k0 + kc;
+        const int valid = (h < p.H && k < p.T) ? 8 : 0;
+        const double *src = valid ? (A + h * p.iah + k) : A;
+        cp_async(dA + r * DM_LDA + kc, src, valid, false);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int c = tid + i * 256;
+        const int r = c >> 7, wc = c & 127;
+        const int64_t k = k0 + r, w = w0 + wc;
+        const int valid = (k < p.T && w < p.W) ? 8 : 0;
+        const double *src = valid ? (B + k * p.ibt + w) : B;
+        cp_async(dB + r * DM_LDB + wc, src, valid, false);
+      }
+    }
+  };
+
+  double acc[8][4][2];   // [m8 tile][n8 tile][col pair]
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+  for (int s = 0; s < DM_STAGES - 1; s++) {
+    if (s < KT) load_tile(s, s);
+    cp_commit();
+  }
+
+  for (int kt = 0; kt < KT; kt++) {
+    cp_wait<DM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + DM_STAGES - 1;
+      if (nk < KT) load_tile(nk, nk % DM_STAGES);
+      cp_commit();
+    }
+    const double *tA = sA + (kt % DM_STAGES) * DM_A_STAGE + (wm * 64) * DM_LDA;
+    const double *tB = sB + (kt % DM_STAGES) * DM_B_STAGE + wn * 32;
+#pragma unroll
+    for (int ks = 0; ks < DM_BK; ks += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) af[i] = tA[(i * 8 + g) * DM_LDA + ks + t4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) bf[j] = tB[(ks + t4) * DM_LDB + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_wait<0>();
+
+  // epilogue: each lane owns C[h][w..w+1] pairs
+  const bool c_vec = (p.icw == 1) && ((((uintptr_t)C) & 15) == 0) && ((p.ich & 1) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int64_t h = h0 + wm * 64 + i * 8 + g;
+    if (h >= p.H) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t w = w0 + wn * 32 + j * 8 + t4 * 2;
+      if (w >= p.W) continue;
+      double *dst = C + h * p.ich + w * p.icw;
+      if (c_vec && w + 1 < p.W) {
+        *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        dst[0] = acc[i][j][0];
+        if (w + 1 < p.W) dst[p.icw] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
+  // eligibility: unit stride along t in a and along w in b (PDL's default physical layout)
+  if (p.T == 0) return PDLB200_EUNSUPPORTED;
+  if (!((p.iat == 1 || p.T == 1) && (p.ibw == 1 || p.W == 1))) return PDLB200_EUNSUPPORTED;
+  if (p.H * p.W < 64 * 64) return PDLB200_EUNSUPPORTED;   // tiny products: the exact kernel is as fast and bit-exact
+  static bool attr_set[2] = {false, false};
+  bool aligned = ((((uintptr_t)p.a) | ((uintptr_t)p.b)) & 15) == 0 && (p.iah % 2 == 0) && (p.ibt % 2 == 0) &&
+                 p.iat == 1 && p.ibw == 1;
+  for (int d = 0; d < p.nd && aligned; d++) if ((p.sa[d] % 2) || (p.sb[d] % 2)) aligned = false;
+  dim3 grid((unsigned)((p.W + DM_BN - 1) / DM_BN), (unsigned)((p.H + DM_BM - 1) / DM_BM), (unsigned)p.nbatch);
+  cudaStream_t s = (cudaStream_t)t->stream;
+  if (aligned) {
+    if (!attr_set[0]) { PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM), E); attr_set[0] = true; }
+    mm_dmma_kernel<true><<<grid, 256, DM_SMEM, s>>>(p);
+  } else {
+    if (!attr_set[1]) { PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM), E); attr_set[1] = true; }
+    mm_dmma_kernel<false><<<grid, 256, DM_SMEM, s>>>(p);
+  }
+  note_launch(aligned ? "matmult_dmma_v16" : "matmult_dmma_v8");
+  PDLB200_CUDA_OK(cudaGetLastError(), E);
+  return PDLB200_OK;
+}
+
+}  // namespace pdlb200

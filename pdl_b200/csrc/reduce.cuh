@@ -13,11 +13,14 @@
 //                                dim is the unit-stride one: adjacent threads read
 //                                adjacent rows, so the loads coalesce across the warp)
 // When there are too few rows to fill 148 SMs each row is cut into chunks
-// (blockIdx.y); partial accumulators go to scratch and a second tiny kernel merges
-// them in chunk order.  All reducers are order-independent restatements of the
-// reference's sequential loop (see each reducer), so integer, min/max and index
-// results are bit-exact however the row is cut; float sums differ only by
-// summation order.
+// (blockIdx.y); partial accumulators go to scratch and a second tiny kernel merges them.
+//
+// Every reducer has two accumulators: a lean per-thread `Loc` that is exactly the
+// reference's sequential loop body applied to that thread's elements in increasing index
+// order (a few instructions per element: the kernels stay HBM-bound), and a cross-thread
+// `Acc` whose merge is an order-independent restatement of the same loop (see each reducer).
+// Integer, min/max and index results are therefore bit-exact however a row is cut; float
+// sums differ from the reference only by summation order.
 #pragma once
 #include "common.cuh"
 
@@ -32,7 +35,7 @@ struct RdPlan {
   int64_t nrows;
   int64_t dims[MAXD];
   int64_t sa[MAXD], sb[MAXD];   // broadcast strides of a and b (elements)
-  int64_t chunk;                // elements of n per chunk (== n when nchunks == 1)
+  int64_t chunk;                // elements of n per chunk (== n when nchunks == 1); always < 2^31
   char *partial;                // scratch for nchunks > 1
   uint64_t abad, bbad;
   int nd;
@@ -58,27 +61,53 @@ template <class O> __device__ __forceinline__ O wrap_add(O a, O b) {
 template <class O> __device__ __forceinline__ O wrap_mul(O a, O b) {
   if constexpr (tt<O>::is_int) { using U = typename tt<O>::wide_u; return (O)((U)a * (U)b); } else return a * b;
 }
+template <class T> __device__ __forceinline__ T nan_of() {
+  if constexpr (sizeof(T) == 4) return __uint_as_float(0x7fc00000u); else return __longlong_as_double(0x7ff8000000000000ll);
+}
+
+constexpr int64_t RD_NOIDX = 0x7fffffffffffffffll;
 
 // ---- reducers -------------------------------------------------------------------
-// Each: Acc, init(), push(acc, value, n-index), merge(l, r) [commutative], finish(acc, n_good-known?, out...)
+// Loc: linit(), lpush(loc, value, rel) with rel = element index - chunk start (int32, increasing
+// per thread); lift(loc, lo) -> Acc.  Acc: init(), merge(l, r) [commutative+associative],
+// finish(acc, plan, out).  kPrefix: the reducer needs the prodover early-exit second phase.
 
 // sumover / dsumover: tmp += a over good elements; no good element in bad mode -> BAD (Ufunc.pd:102-110)
 template <class T, class O> struct RSum {
+  static constexpr bool kPrefix = false;
+  struct Loc { O s; int32_t any; };
   struct Acc { O s; int32_t any; int32_t pad; };
+  static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.any = 0; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.any = 1; }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.s = l.s; x.any = l.any; x.pad = 0; return x; }
   static __device__ __forceinline__ Acc init() { Acc x; x.s = O(0); x.any = 0; x.pad = 0; return x; }
-  static __device__ __forceinline__ void push(Acc &x, T v, int64_t) { x.s = wrap_add<O>(x.s, (O)v); x.any = 1; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = wrap_add<O>(l.s, r.s); x.any = l.any | r.any; x.pad = 0; return x; }
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) {
     *out = (p.badmode && !x.any) ? from_bits<O>(p.bbad) : x.s;
   }
 };
-// prodover / dprodover (Ufunc.pd:91,102-110).  The reference leaves the loop once tmp == 0; for
-// integers and finite floats the product is the same with or without the early exit.
+// prodover / dprodover (Ufunc.pd:91,102-110): `tmp *= a; if (tmp == 0) break;`.  For integer
+// outputs 0 absorbs everything, so the plain wrapped product is already the answer.  For float
+// outputs the loop stops at the first zero element z, so the answer is prod(a[0..z]) — the sign of
+// the zero comes from the prefix only, and an inf/NaN prefix gives NaN (inf*0) which never compares
+// equal to 0, so the loop runs on and stays NaN.  z is reduced here (min); the kernel then runs a
+// second pass over [0, z) for rows that have one (kPrefix).
 template <class T, class O> struct RProd {
-  struct Acc { O s; int32_t any; int32_t pad; };
-  static __device__ __forceinline__ Acc init() { Acc x; x.s = O(1); x.any = 0; x.pad = 0; return x; }
-  static __device__ __forceinline__ void push(Acc &x, T v, int64_t) { x.s = wrap_mul<O>(x.s, (O)v); x.any = 1; }
-  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = wrap_mul<O>(l.s, r.s); x.any = l.any | r.any; x.pad = 0; return x; }
+  static constexpr bool kPrefix = !tt<O>::is_int;
+  struct Loc { O s; int32_t any; int32_t z; };
+  struct Acc { O s; int32_t any; int32_t pad; int64_t z; };
+  static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(1); x.any = 0; x.z = 0x7fffffff; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t rel) {
+    x.s = wrap_mul<O>(x.s, (O)v); x.any = 1;
+    if constexpr (kPrefix) { if ((O)v == O(0) && rel < x.z) x.z = rel; }
+  }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t lo) {
+    Acc x; x.s = l.s; x.any = l.any; x.pad = 0; x.z = (l.z == 0x7fffffff) ? RD_NOIDX : lo + l.z; return x;
+  }
+  static __device__ __forceinline__ Acc init() { Acc x; x.s = O(1); x.any = 0; x.pad = 0; x.z = RD_NOIDX; return x; }
+  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
+    Acc x; x.s = wrap_mul<O>(l.s, r.s); x.any = l.any | r.any; x.pad = 0; x.z = l.z < r.z ? l.z : r.z; return x;
+  }
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) {
     *out = (p.badmode && !x.any) ? from_bits<O>(p.bbad) : x.s;
   }
@@ -86,15 +115,19 @@ template <class T, class O> struct RProd {
 // average / daverage (Ufunc.pd:417-430): tmp / cnt evaluated with C's usual arithmetic
 // conversions (cnt is PDL_Indx = int64); cnt == 0 -> BAD (bad mode) or 0 / NaN (good mode).
 template <class T, class O> struct RAvg {
+  static constexpr bool kPrefix = false;
+  struct Loc { O s; int32_t cnt; };
   struct Acc { O s; int64_t cnt; };
+  static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.cnt = 0; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.cnt++; }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.s = l.s; x.cnt = l.cnt; return x; }
   static __device__ __forceinline__ Acc init() { Acc x; x.s = O(0); x.cnt = 0; return x; }
-  static __device__ __forceinline__ void push(Acc &x, T v, int64_t) { x.s = wrap_add<O>(x.s, (O)v); x.cnt++; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = wrap_add<O>(l.s, r.s); x.cnt = l.cnt + r.cnt; return x; }
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) {
     if (x.cnt == 0) {
       if (p.badmode) *out = from_bits<O>(p.bbad);
       else if constexpr (tt<O>::is_int) *out = O(0);
-      else *out = (O)__longlong_as_double(0x7ff8000000000000ll);  // NAN
+      else *out = nan_of<O>();
       return;
     }
     if constexpr (!tt<O>::is_int) *out = x.s / (O)x.cnt;
@@ -103,17 +136,34 @@ template <class T, class O> struct RAvg {
   }
 };
 // minimum / maximum / _ind (Ufunc.pd:455-465,481-491).  Sequential rule: cur is replaced when
-// (a OP cur) or cur is NaN.  Closed form: the first-in-index-order extreme of the non-NaN good
-// values; if every good value is NaN, the LAST NaN; if there is no good value, BAD.
+// (a OP cur) or cur is NaN (or nothing was taken yet).  Loc applies exactly that rule, with "nothing
+// yet" encoded as idx < 0 (and cur = NaN for float types so one test covers both).  Closed form used
+// by the merge: the first-in-index-order extreme of the non-NaN good values; if every good value is
+// NaN, the LAST NaN; if there is no good value, BAD.
 template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
+  static constexpr bool kPrefix = false;
+  struct Loc { T cur; int32_t idx; };
   struct Acc { T cur; int64_t idx; int32_t state; int32_t pad; };  // state 0 empty, 1 non-NaN, 2 NaN only
+  static __device__ __forceinline__ Loc linit() {
+    Loc x; x.idx = -1;
+    if constexpr (tt<T>::is_int) x.cur = T(0); else x.cur = nan_of<T>();
+    return x;
+  }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t rel) {
+    bool take;
+    if constexpr (tt<T>::is_int) take = (ISMAX ? (v > x.cur) : (v < x.cur)) || (x.idx < 0);
+    else take = (ISMAX ? (v > x.cur) : (v < x.cur)) || (x.cur != x.cur);
+    x.cur = take ? v : x.cur;
+    x.idx = take ? rel : x.idx;
+  }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t lo) {
+    Acc x; x.cur = l.cur; x.idx = l.idx < 0 ? -1 : lo + l.idx; x.pad = 0;
+    x.state = l.idx < 0 ? 0 : (t_isnan(l.cur) ? 2 : 1);
+    return x;
+  }
   static __device__ __forceinline__ Acc init() { Acc x; x.cur = T(0); x.idx = -1; x.state = 0; x.pad = 0; return x; }
   static __device__ __forceinline__ bool better(T v, int64_t i, T cur, int64_t idx) {
     return (ISMAX ? (v > cur) : (v < cur)) || (v == cur && i < idx);
-  }
-  static __device__ __forceinline__ void push(Acc &x, T v, int64_t i) {
-    if (t_isnan(v)) { if (x.state == 0 || (x.state == 2 && i > x.idx)) { x.cur = v; x.idx = i; x.state = 2; } }
-    else if (x.state != 1 || better(v, i, x.cur, x.idx)) { x.cur = v; x.idx = i; x.state = 1; }
   }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
     if (r.state == 0) return l;
@@ -132,15 +182,19 @@ template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
 // andover orover zcover xorover (logical) and bandover borover bxorover (bitwise), Ufunc.pd:143-187.
 // KIND: 0 and, 1 or, 2 zc, 3 xor, 4 band, 5 bor, 6 bxor.  Output type == input type.
 template <class T, int KIND> struct RBits {
-  struct Acc { typename tt<T>::wide_u v; int32_t any; };
+  static constexpr bool kPrefix = false;
   using U = typename tt<T>::wide_u;
+  struct Acc { U v; int32_t any; };
+  using Loc = Acc;
   static __device__ __forceinline__ Acc init() {
     Acc x; x.any = 0;
     x.v = (KIND == 0 || KIND == 2) ? U(1) : (KIND == 4) ? ~U(0) : U(0);
     return x;
   }
+  static __device__ __forceinline__ Loc linit() { return init(); }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { return l; }
   static __device__ __forceinline__ U bits(T a) { if constexpr (tt<T>::is_int) return (U)a; else return U(0); }
-  static __device__ __forceinline__ void push(Acc &x, T a, int64_t) {
+  static __device__ __forceinline__ void lpush(Acc &x, T a, int32_t) {
     x.any = 1;
     if constexpr (KIND == 0) x.v &= U(a != 0);
     else if constexpr (KIND == 1) x.v |= U(a != 0);
@@ -164,54 +218,56 @@ template <class T, int KIND> struct RBits {
 
 // ---- row walk -------------------------------------------------------------------
 template <class R, class T, bool BAD>
-__device__ __forceinline__ void rd_push(typename R::Acc &acc, T v, int64_t i, T abad, bool abadnan) {
+__device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad, bool abadnan) {
   if constexpr (BAD) { if (is_bad(v, abad, abadnan)) return; }
-  R::push(acc, v, i);
+  R::lpush(loc, v, rel);
 }
 
-// Accumulate elements [lo, hi) of one row; `lane` of `width` cooperating threads.
+// Accumulate elements [lo, hi) of one row (hi - lo < 2^31); `lane` of `width` cooperating threads.
+// Each thread visits its elements in increasing index order.
 template <class R, class T, bool BAD>
-__device__ __forceinline__ void rd_row(typename R::Acc &acc, const T *row, int64_t lo, int64_t hi, int64_t inc,
+__device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64_t lo, int64_t hi, int64_t inc,
                                        int lane, int width, T abad, bool abadnan) {
   constexpr int VEC = 16 / sizeof(T);
+  const T *base = row + lo * inc;         // element `rel` lives at base[rel * inc]
+  const int32_t len = (int32_t)(hi - lo);
   if (inc == 1) {
     // peel to 16-byte alignment, then 128-bit loads with RD_UNROLL in flight, then the tail
-    const uintptr_t addr = (uintptr_t)(row + lo);
-    int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));
-    if (head > hi - lo) head = hi - lo;
-    for (int64_t i = lo + lane; i < lo + head; i += width) rd_push<R, T, BAD>(acc, row[i], i, abad, abadnan);
-    const int64_t v0 = lo + head;
-    const int64_t nv = (hi - v0) / VEC;
-    const uint4 *vp = reinterpret_cast<const uint4 *>(row + v0);
-    int64_t j = lane;
-    for (; j + (int64_t)(RD_UNROLL - 1) * width < nv; j += (int64_t)RD_UNROLL * width) {
+    const uintptr_t addr = (uintptr_t)base;
+    int32_t head = (int32_t)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > len) head = len;
+    for (int32_t i = lane; i < head; i += width) rd_push<R, T, BAD>(loc, base[i], i, abad, abadnan);
+    const int32_t nv = (len - head) / VEC;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(base + head);
+    int32_t j = lane;
+    for (; j + (RD_UNROLL - 1) * width < nv; j += RD_UNROLL * width) {
       Pack<T> r[RD_UNROLL];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) r[u].q = vp[j + (int64_t)u * width];
+      for (int u = 0; u < RD_UNROLL; u++) r[u].q = vp[j + u * width];
 #pragma unroll
       for (int u = 0; u < RD_UNROLL; u++) {
-        const int64_t e0 = v0 + (j + (int64_t)u * width) * VEC;
+        const int32_t e0 = head + (j + u * width) * VEC;
 #pragma unroll
-        for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(acc, r[u].e[k], e0 + k, abad, abadnan);
+        for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(loc, r[u].e[k], e0 + k, abad, abadnan);
       }
     }
     for (; j < nv; j += width) {
       Pack<T> r; r.q = vp[j];
-      const int64_t e0 = v0 + j * VEC;
+      const int32_t e0 = head + j * VEC;
 #pragma unroll
-      for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(acc, r.e[k], e0 + k, abad, abadnan);
+      for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(loc, r.e[k], e0 + k, abad, abadnan);
     }
-    for (int64_t i = v0 + nv * VEC + lane; i < hi; i += width) rd_push<R, T, BAD>(acc, row[i], i, abad, abadnan);
+    for (int32_t i = head + nv * VEC + lane; i < len; i += width) rd_push<R, T, BAD>(loc, base[i], i, abad, abadnan);
   } else {
-    int64_t i = lo + lane;
-    for (; i + (int64_t)(RD_UNROLL - 1) * width < hi; i += (int64_t)RD_UNROLL * width) {
+    int32_t i = lane;
+    for (; i + (RD_UNROLL - 1) * width < len; i += RD_UNROLL * width) {
       T v[RD_UNROLL];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) v[u] = row[(i + (int64_t)u * width) * inc];
+      for (int u = 0; u < RD_UNROLL; u++) v[u] = base[(int64_t)(i + u * width) * inc];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) rd_push<R, T, BAD>(acc, v[u], i + (int64_t)u * width, abad, abadnan);
+      for (int u = 0; u < RD_UNROLL; u++) rd_push<R, T, BAD>(loc, v[u], i + u * width, abad, abadnan);
     }
-    for (; i < hi; i += width) rd_push<R, T, BAD>(acc, row[i * inc], i, abad, abadnan);
+    for (; i < len; i += width) rd_push<R, T, BAD>(loc, base[(int64_t)i * inc], i, abad, abadnan);
   }
 }
 
@@ -228,6 +284,47 @@ __device__ __forceinline__ void rd_row_offsets(const RdPlan &p, int64_t row, int
   }
 }
 
+// Reduce `acc` over the cooperating group; on return every thread of the group holds the total.
+// MODE 2 uses `smem` (RD_THREADS/32 + 1 slots) and two barriers.
+template <class R, int MODE>
+__device__ __forceinline__ typename R::Acc rd_group_reduce(typename R::Acc acc, typename R::Acc *smem) {
+  if (MODE >= 1) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
+  }
+  if (MODE == 2) {
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) smem[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+      acc = (threadIdx.x < RD_THREADS / 32) ? smem[threadIdx.x] : R::init();
+#pragma unroll
+      for (int m = (RD_THREADS / 64); m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
+      if (threadIdx.x == 0) smem[RD_THREADS / 32] = acc;
+    }
+    __syncthreads();
+    acc = smem[RD_THREADS / 32];
+    __syncthreads();  // smem is reused by the next reduction
+  }
+  return acc;
+}
+
+// prodover second phase: the product of the good elements of [0, z) times a[z], by the group.
+template <class R, class T, class O, bool BAD, int MODE>
+__device__ __forceinline__ O rd_prod_prefix(const T *row, int64_t z, int64_t inc, int lane, int width,
+                                            T abad, bool abadnan, typename RProd<T, O>::Acc *smem) {
+  using P = RProd<T, O>;
+  typename P::Acc tot = P::init();
+  for (int64_t lo = 0; lo < z; lo += 0x40000000ll) {
+    const int64_t hi = (lo + 0x40000000ll < z) ? lo + 0x40000000ll : z;
+    typename P::Loc loc = P::linit();
+    rd_row<P, T, BAD>(loc, row, lo, hi, inc, lane, width, abad, abadnan);
+    tot = P::merge(tot, P::lift(loc, lo));
+  }
+  tot = rd_group_reduce<P, MODE>(tot, smem);
+  return tot.s * (O)row[z * inc];
+}
+
 // MODE: 0 thread/row, 1 warp/row, 2 CTA/row.  blockIdx.y = chunk of n.
 template <class R, class T, class O, bool BAD, int MODE>
 __global__ void __launch_bounds__(RD_THREADS)
@@ -238,7 +335,7 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
   const int chunk_id = blockIdx.y;
   const int64_t lo = (int64_t)chunk_id * p.chunk;
   const int64_t hi = (lo + p.chunk < p.n) ? lo + p.chunk : p.n;
-  __shared__ Acc smem[RD_THREADS / 32];
+  __shared__ Acc smem[RD_THREADS / 32 + 1];
 
   int64_t row, row_step; int lane, width;
   if (MODE == 0) { row = (int64_t)blockIdx.x * RD_THREADS + threadIdx.x; row_step = (int64_t)gridDim.x * RD_THREADS; lane = 0; width = 1; }
@@ -248,35 +345,29 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
   for (; row < p.nrows; row += row_step) {
     int64_t oa, ob;
     rd_row_offsets(p, row, oa, ob);
-    Acc acc = R::init();
-    rd_row<R, T, BAD>(acc, reinterpret_cast<const T *>(p.a) + oa, lo, hi, p.inc_n, lane, width, abad, abadnan);
-    bool writer = true;
-    if (MODE >= 1) {
-#pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
-      writer = (lane & 31) == 0;
-    }
-    if (MODE == 2) {
-      const int w = threadIdx.x >> 5;
-      if ((threadIdx.x & 31) == 0) smem[w] = acc;
-      __syncthreads();
-      if (w == 0) {
-        acc = (threadIdx.x < RD_THREADS / 32) ? smem[threadIdx.x] : R::init();
-#pragma unroll
-        for (int m = (RD_THREADS / 64); m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
+    const T *rp = reinterpret_cast<const T *>(p.a) + oa;
+    typename R::Loc loc = R::linit();
+    rd_row<R, T, BAD>(loc, rp, lo, hi, p.inc_n, lane, width, abad, abadnan);
+    Acc acc = rd_group_reduce<R, MODE>(R::lift(loc, lo), smem);
+    const bool writer = (MODE == 0) || (MODE == 1 && lane == 0) || (MODE == 2 && threadIdx.x == 0);
+    if (p.nchunks == 1) {
+      O *out = reinterpret_cast<O *>(p.b) + ob;
+      if constexpr (R::kPrefix) {
+        if (acc.z != RD_NOIDX) {   // uniform over the group: every thread holds the total
+          const O v = rd_prod_prefix<R, T, O, BAD, MODE>(rp, acc.z, p.inc_n, lane, width, abad, abadnan, smem);
+          if (writer) *out = v;
+          continue;
+        }
       }
-      writer = threadIdx.x == 0;
-      __syncthreads();  // smem reused by the next row
-    }
-    if (writer) {
-      if (p.nchunks == 1) R::finish(acc, p, reinterpret_cast<O *>(p.b) + ob);
-      else reinterpret_cast<Acc *>(p.partial)[row * p.nchunks + chunk_id] = acc;
+      if (writer) R::finish(acc, p, out);
+    } else if (writer) {
+      reinterpret_cast<Acc *>(p.partial)[row * p.nchunks + chunk_id] = acc;
     }
   }
 }
 
 // second stage: one warp per row merges that row's partials
-template <class R, class O>
+template <class R, class T, class O, bool BAD>
 __global__ void __launch_bounds__(RD_THREADS)
 reduce_finish_kernel(const __grid_constant__ RdPlan p) {
   using Acc = typename R::Acc;
@@ -291,7 +382,16 @@ reduce_finish_kernel(const __grid_constant__ RdPlan p) {
     for (int c = lane; c < p.nchunks; c += 32) acc = R::merge(acc, part[c]);
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
-    if (lane == 0) R::finish(acc, p, reinterpret_cast<O *>(p.b) + ob);
+    O *out = reinterpret_cast<O *>(p.b) + ob;
+    if constexpr (R::kPrefix) {
+      if (acc.z != RD_NOIDX) {
+        const T *rp = reinterpret_cast<const T *>(p.a) + oa;
+        const O v = rd_prod_prefix<R, T, O, BAD, 1>(rp, acc.z, p.inc_n, lane, 32, from_bits<T>(p.abad), p.abadnan != 0, nullptr);
+        if (lane == 0) *out = v;
+        continue;
+      }
+    }
+    if (lane == 0) R::finish(acc, p, out);
   }
 }
 
@@ -317,7 +417,8 @@ int rd_launch_typed(const pdlb200_trans *t, const char *name, const Err &E) {
     int64_t g = (p.nrows + RD_THREADS / 32 - 1) / (RD_THREADS / 32);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (g > cap) g = cap;
-    reduce_finish_kernel<R, O><<<(int)g, RD_THREADS, 0, s>>>(p);
+    if (t->bvalflag) reduce_finish_kernel<R, T, O, true><<<(int)g, RD_THREADS, 0, s>>>(p);
+    else reduce_finish_kernel<R, T, O, false><<<(int)g, RD_THREADS, 0, s>>>(p);
     note_launch("reduce_finish");
     PDLB200_CUDA_OK(cudaGetLastError(), E);
   }

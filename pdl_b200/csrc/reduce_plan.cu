@@ -62,6 +62,12 @@ int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_
       p->nchunks = (int)((n + chunk - 1) / chunk);
     }
   }
+  // per-thread element indices are 32-bit relative to the chunk start: keep chunks below 2^30
+  if (p->chunk > (1ll << 30)) {
+    const int64_t want = (n + (1ll << 30) - 1) >> 30;
+    int64_t chunk = (n + want - 1) / want; chunk = (chunk + 4095) / 4096 * 4096;
+    p->chunk = chunk; p->nchunks = (int)((n + chunk - 1) / chunk);
+  }
   if (const char *e = getenv("PDLB200_REDUCE_CHUNKS")) {
     int want = atoi(e);
     if (want >= 1 && want <= 65535 && n > 0) {

@@ -4,8 +4,4 @@ namespace pdlb200 {
 int launch_scan(const pdlb200_trans *t, const Err &E) {
   return E.fail(PDLB200_EUNSUPPORTED, "%s: scans are not on the device path yet", pdlb200_op_name(t->op));
 }
-struct MmPlan;
-int launch_matmult_dmma(const pdlb200_trans *, const MmPlan &, const Err &E) {
-  return E.fail(PDLB200_EUNSUPPORTED, "matmult: tensor-core path not built");
-}
 }  // namespace pdlb200

@@ -99,7 +99,12 @@ def check_case(case, engine):
     got = out.to_numpy().reshape(-1)
     exp = np.frombuffer(bytes.fromhex(want["hex"]), dtype=dt)
     tol = case.get("tol_ulp")
-    if tol and dt.kind == "f":
+    # float sum/product/average: a NaN result is NaN on both sides, but its sign/payload is an
+    # artefact of summation order and of x86-vs-GPU NaN generation, not of PDL semantics
+    nan_free = case["call"]["kind"] in ("reduce", "whole") and any(
+        k in case["call"]["op"] for k in ("sum", "prod", "aver", "avg"))
+    if dt.kind == "f" and (tol or nan_free):
+        tol = tol or 0
         d = ulp_diff(got, exp)
         assert d <= tol, (case["name"], f"{d} ulp > {tol}", got, exp)
     else:

@@ -1,0 +1,51 @@
+"""CPU: the C-ABI library loads, exports every symbol include/pdlb200.h declares, and its
+compute entry points FAIL LOUDLY without a GPU (no CPU fallback)."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+from pdl_b200 import _abi
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_header_symbols_all_exported():
+    hdr = (ROOT / "include" / "pdlb200.h").read_text()
+    declared = set(re.findall(r"PDLB200_API[^;]*?\b(pdlb200_\w+)\s*\(", hdr))
+    assert declared, "no PDLB200_API prototypes found"
+    assert declared == set(_abi.SYMBOLS)
+    lib = _abi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_layout_matches_header():
+    # sizes computed from the header's field list (LP64)
+    assert C.sizeof(_abi.Par) == 8 + 8 + 8 + 4 + 4
+    assert C.sizeof(_abi.Trans) == 6 * 4 + 16 * 8 + 64 * 8 + 4 * 8 + 8 * 8 + 4 * C.sizeof(_abi.Par) + 8
+
+
+def test_plumbing_without_gpu():
+    lib = _abi.load()
+    assert lib.pdlb200_abi_version() == 1
+    assert lib.pdlb200_type_size(10) == 8 and lib.pdlb200_type_size(0) == 1
+    assert lib.pdlb200_op_name(30) == b"sumover"
+    if lib.pdlb200_device_count() > 0:
+        pytest.skip("a GPU is present; the no-device behaviour is checked on CPU boxes")
+    err = C.create_string_buffer(256)
+    tr = _abi.Trans()
+    tr.op, tr.datatype, tr.npdls, tr.ndims = 0, 10, 3, 1
+    rc = lib.pdlb200_readdata(C.byref(tr), err, 256)
+    assert rc == _abi.ENODEVICE
+    assert b"no CPU fallback" in err.value
+
+
+def test_engine_refuses_without_gpu():
+    import pdl_b200 as P
+    lib = _abi.load()
+    if lib.pdlb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(P.PDLError):
+        P.CudaEngine()

@@ -1,0 +1,249 @@
+"""GPU parity proper: CUDA path (through the C-ABI) vs the oracle on seeded inputs at sizes the
+oracle finishes in seconds, covering the kernel variants the golden fixtures are too small
+to reach (128-bit vector bodies and tails, grid-stride, every reduce mode, split rows)."""
+import os
+
+import numpy as np
+import pytest
+
+import pdl_b200 as P
+from pdl_b200 import types as T, ufunc
+from parity import ALL_TYPES, INT_TYPES, assert_same, both, rand_array
+
+pytestmark = pytest.mark.gpu
+
+BIOPS_ALL = ["plus", "mult", "minus", "gt", "lt", "le", "ge", "eq", "ne", "spaceship"]
+BIOPS_INT = ["or2", "and2", "xor"]
+
+
+@pytest.fixture()
+def engines(cuda_engine, oracle_engine):
+    return [cuda_engine, oracle_engine]
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_biops_contiguous_odd_size(engines, t):
+    rng = np.random.default_rng(100 + t)
+    n = 1_000_003  # not a multiple of any vector width: exercises the tail unit
+    a, b = rand_array(rng, t, (n,)), rand_array(rng, t, (n,))
+    for op in BIOPS_ALL + (BIOPS_INT if t in T.INTEGER else []):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"{op}-{T.NAMES[t]}", P.run_biop(op, ga, gb), P.run_biop(op, oa, ob))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_divide_modulo(engines, t):
+    rng = np.random.default_rng(200 + t)
+    a, b = rand_array(rng, t, (300_001,)), rand_array(rng, t, (300_001,), "pos")
+    if t not in T.UNSIGNED:
+        b = (b * rng.choice(np.array([-1, 1], dtype=b.dtype), size=b.shape)).astype(b.dtype)
+        if t in T.INTEGER:
+            b[b == -1] = 3  # INT_MIN / -1 kills the reference (SIGFPE): no reference answer
+    for op in ("divide", "modulo"):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"{op}-{T.NAMES[t]}", P.run_biop(op, ga, gb), P.run_biop(op, oa, ob))
+
+
+@pytest.mark.parametrize("t", INT_TYPES, ids=lambda t: T.NAMES[t])
+def test_shifts(engines, t):
+    rng = np.random.default_rng(300 + t)
+    width = max(32, T.SIZE[t] * 8)
+    a = rand_array(rng, t, (100_003,))
+    cnt = rng.integers(0, min(width - 2, 62), size=a.shape, endpoint=True).astype(T.NP_DTYPE[t])
+    for op in ("shiftleft", "shiftright"):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, cnt, t)
+        assert_same(f"{op}-{T.NAMES[t]}", P.run_biop(op, ga, gb), P.run_biop(op, oa, ob))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_bad_values_elementwise(engines, t):
+    rng = np.random.default_rng(400 + t)
+    a, b = rand_array(rng, t, (513, 257), "small"), rand_array(rng, t, (513, 257), "pos")
+    bad = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+    a[rng.random(a.shape) < 0.05] = bad
+    b[rng.random(b.shape) < 0.05] = bad
+    for op in ("plus", "mult", "divide", "lt", "modulo"):
+        (ga, oa), (gb, ob) = both(engines, a, t, True), both(engines, b, t, True)
+        assert_same(f"bad-{op}-{T.NAMES[t]}", P.run_biop(op, ga, gb), P.run_biop(op, oa, ob))
+    (ga, oa) = both(engines, a, t, True)
+    assert_same(f"bad-abs-{T.NAMES[t]}", P.run_ufunc("_rabs", ga), P.run_ufunc("_rabs", oa))
+
+
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_float_ieee_specials_bit_exact(engines, t):
+    rng = np.random.default_rng(500 + t)
+    n = 200_001
+    a, b = rand_array(rng, t, (n,)), rand_array(rng, t, (n,))
+    for arr in (a, b):
+        k = rng.integers(0, n, size=2000)
+        arr[k[:400]] = np.inf; arr[k[400:800]] = -np.inf; arr[k[800:1200]] = np.nan
+        arr[k[1200:1600]] = 0.0; arr[k[1600:]] = -0.0
+    a[::7] *= np.finfo(T.NP_DTYPE[t]).tiny  # denormal products / quotients
+    for op in ("plus", "minus", "mult", "divide"):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"{op}-{T.NAMES[t]}", P.run_biop(op, ga, gb), P.run_biop(op, oa, ob))
+    pos = np.abs(a)
+    (ga, oa) = both(engines, pos, t)
+    assert_same(f"sqrt-{T.NAMES[t]}", P.run_ufunc("sqrt", ga), P.run_ufunc("sqrt", oa))
+
+
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_transcendentals_within_ulp(engines, t):
+    # glibc libm vs CUDA libdevice: documented max error of the CUDA functions is <= 2 ulp (float)
+    # / <= 2 ulp (double) for these; glibc is <= 1 ulp.  Tolerance: 4 ulp.
+    rng = np.random.default_rng(600 + t)
+    a = rand_array(rng, t, (100_001,), "small")
+    pos = rand_array(rng, t, (100_001,), "pos")
+    for op, src in (("sin", a), ("cos", a), ("exp", a), ("log", pos), ("log10", pos)):
+        (ga, oa) = both(engines, src, t)
+        assert_same(f"{op}-{T.NAMES[t]}", P.run_ufunc(op, ga), P.run_ufunc(op, oa), tol_ulp=4)
+    (ga, oa), (gb, ob) = both(engines, pos, t), both(engines, a, t)
+    assert_same(f"power-{T.NAMES[t]}", P.run_biop("power", ga, gb), P.run_biop("power", oa, ob), tol_ulp=4)
+    assert_same(f"atan2-{T.NAMES[t]}", P.run_biop("atan2", gb, ga), P.run_biop("atan2", ob, oa), tol_ulp=4)
+
+
+def test_views_strided_dummy_negative(engines):
+    rng = np.random.default_rng(700)
+    big1, big2 = rand_array(rng, T.D, (4096,)), rand_array(rng, T.D, (4096,))
+    outs = []
+    for e in engines:
+        a = P.PDL.from_numpy(big1, T.D, e).slice("0:-1:2").dummy(1, 1)
+        b = P.PDL.from_numpy(big2, T.D, e).slice("0:-1:2").dummy(0, 1)
+        outs.append(ufunc.sumover(a * b))
+    assert_same("cfg3-small", outs[0], outs[1], tol_ulp=0)
+    m = rand_array(rng, T.L, (301, 203))
+    outs = []
+    for e in engines:
+        p = P.PDL.from_numpy(m, T.L, e)
+        outs.append(p.slice("-1:0,:") - p.slice(":,-1:0") + p.xchg(0, 1).slice("(5),:").dummy(1, 1))
+    assert_same("neg-strides", outs[0], outs[1])
+    v = rand_array(rng, T.F, (4, 1, 33, 1, 5))
+    w = rand_array(rng, T.F, (1, 6, 1, 7, 5))
+    outs = [P.PDL.from_numpy(v, T.F, e) + P.PDL.from_numpy(w, T.F, e) for e in engines]
+    assert_same("5d-broadcast", outs[0], outs[1])
+    outs = []
+    for e in engines:  # unaligned base offset: vector path must fall back per operand
+        p = P.PDL.from_numpy(big1, T.D, e)
+        outs.append(p.slice("1:-2") + p.slice("2:-1"))
+    assert_same("unaligned-offset", outs[0], outs[1])
+    outs = []
+    for e in engines:  # inplace on a strided view writes through to the parent
+        p = P.PDL.from_numpy(big1, T.D, e)
+        v2 = p.slice("1:-1:3")
+        v2 += 2.5
+        outs.append(p + 0)
+    assert_same("inplace-through-view", outs[0], outs[1])
+
+
+NAN_FREE = {"sumover", "prodover", "dsumover", "dprodover", "average", "daverage"}
+REDUCERS = ["sumover", "prodover", "dsumover", "average", "daverage", "minimum", "maximum",
+            "minimum_ind", "maximum_ind", "andover", "orover", "zcover", "xorover"]
+# (n, rows): thread-per-row, warp-per-row, CTA-per-row, and few-long-rows (split into chunks)
+SHAPES = [(7, 1500), (33, 700), (1000, 257), (9001, 67), (70_001, 3), (300_007, 1)]
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"n{s[0]}x{s[1]}")
+def test_reductions_all_modes(engines, t, shape):
+    n, rows = shape
+    rng = np.random.default_rng(800 + t + n)
+    a = rand_array(rng, t, (rows, n), "exact" if t in (T.F, T.D) else "mixed")
+    red = REDUCERS + (["bandover", "borover", "bxorover"] if t in T.INTEGER else [])
+    for op in red:
+        src = a
+        if op in ("prodover",) and t in (T.F, T.D):
+            src = np.where(rng.random(a.shape) < 0.5, 1.0, -1.0).astype(a.dtype)  # exact in any order
+        (ga, oa) = both(engines, src, t)
+        assert_same(f"{op}-{T.NAMES[t]}-{n}x{rows}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa),
+                    nan_equal=op in NAN_FREE)
+
+
+@pytest.mark.parametrize("t", [T.B, T.S, T.L, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
+@pytest.mark.parametrize("shape", [(33, 700), (9001, 67), (300_007, 2)], ids=lambda s: f"n{s[0]}x{s[1]}")
+def test_reductions_bad(engines, t, shape):
+    n, rows = shape
+    rng = np.random.default_rng(900 + t + n)
+    a = rand_array(rng, t, (rows, n), "exact" if t in (T.F, T.D) else "small")
+    bad = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+    a[rng.random(a.shape) < 0.01] = bad
+    a[0, :] = bad          # an all-BAD row
+    if t in (T.F, T.D):
+        a[1, ::5] = np.nan; a[1, 3] = -0.0; a[1, 4] = 0.0
+    for op in ("sumover", "average", "daverage", "minimum", "maximum", "minimum_ind", "maximum_ind", "prodover", "orover"):
+        src = a
+        if op == "prodover" and t in (T.F, T.D):
+            src = np.where(np.isin(a, [bad]), bad, np.where(rng.random(a.shape) < 0.5, 1.0, -1.0)).astype(a.dtype)
+        (ga, oa) = both(engines, src, t, True)
+        assert_same(f"bad-{op}-{T.NAMES[t]}-{n}x{rows}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa),
+                    nan_equal=op in NAN_FREE)
+
+
+def test_reduction_views(engines):
+    rng = np.random.default_rng(1000)
+    m = rand_array(rng, T.F, (513, 1025), "exact")
+    outs = []
+    for e in engines:
+        p = P.PDL.from_numpy(m, T.F, e)
+        outs.append([ufunc.sumover(p.xchg(0, 1)), ufunc.maximum_ind(p.slice("-1:0:-3,:")),
+                     ufunc.minimum(p.slice("5:900:7,2:-1:2").xchg(0, 1)), ufunc.average(p.dummy(0, 3).clump(2)),
+                     ufunc.sum(p), ufunc.max(p), ufunc.min(p.slice("1:-1,:"))])
+    for k, (g, w) in enumerate(zip(*outs)):
+        assert_same(f"reduce-view-{k}", g, w)
+
+
+def test_float_sum_tolerance(engines):
+    """Order-dependent float sums: the device tree order vs the reference's sequential order.
+    Stated tolerance: |got - want| <= 2 * n * eps * sum|x| (classic sequential-sum bound)."""
+    rng = np.random.default_rng(1100)
+    for t in (T.F, T.D):
+        a = rand_array(rng, t, (31, 50_000))
+        (ga, oa) = both(engines, a, t)
+        for op in ("sumover", "average"):
+            g, w = getattr(ufunc, op)(ga).to_numpy().astype(np.float64), getattr(ufunc, op)(oa).to_numpy().astype(np.float64)
+            scale = np.abs(a.astype(np.float64)).sum(axis=1) / (a.shape[1] if op == "average" else 1)
+            bound = 2 * a.shape[1] * np.finfo(T.NP_DTYPE[t]).eps * scale
+            assert np.all(np.abs(g - w) <= bound), (op, T.NAMES[t], np.max(np.abs(g - w) / bound))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_matmult_exact_kernel(engines, t):
+    rng = np.random.default_rng(1200 + t)
+    os.environ["PDLB200_MATMULT"] = "exact"
+    try:
+        for (h, tt, w) in [(65, 67, 66), (130, 300, 70), (1, 513, 5)]:
+            a, b = rand_array(rng, t, (h, tt)), rand_array(rng, t, (tt, w))
+            (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+            assert_same(f"matmult-{T.NAMES[t]}-{h}x{tt}x{w}", P.matmult(ga, gb), P.matmult(oa, ob))
+    finally:
+        os.environ.pop("PDLB200_MATMULT", None)
+
+
+def test_matmult_bad_and_batched(engines):
+    rng = np.random.default_rng(1300)
+    for t in (T.L, T.F, T.D):
+        a, b = rand_array(rng, t, (4, 70, 90), "small"), rand_array(rng, t, (90, 33), "small")
+        bad = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        a[rng.random(a.shape) < 0.01] = bad
+        b[rng.random(b.shape) < 0.01] = bad
+        (ga, oa), (gb, ob) = both(engines, a, t, True), both(engines, b, t, True)
+        assert_same(f"matmult-bad-{T.NAMES[t]}", P.matmult(ga, gb), P.matmult(oa, ob))
+    a, b = rand_array(rng, T.D, (200, 96), "small"), rand_array(rng, T.D, (130, 200), "small")
+    outs = [P.matmult(P.PDL.from_numpy(a, T.D, e).xchg(0, 1), P.PDL.from_numpy(b, T.D, e).xchg(0, 1)) for e in engines]
+    assert_same("matmult-transposed-views", outs[0], outs[1])
+
+
+def test_matmult_default_path_double(engines):
+    """Default double path (tensor-core tiles when eligible): exactly representable inputs make
+    every product and partial sum exact, so the result must be BIT-EXACT whatever the order;
+    random inputs must be within K*eps*sum|a||b| of the reference's sequential sum."""
+    rng = np.random.default_rng(1400)
+    h, tt, w = 256, 512, 384
+    a = (rng.integers(-64, 64, size=(h, tt)) / 64).astype(np.float64)
+    b = (rng.integers(-64, 64, size=(tt, w)) / 64).astype(np.float64)
+    (ga, oa), (gb, ob) = both(engines, a, T.D), both(engines, b, T.D)
+    assert_same("matmult-default-exact-inputs", P.matmult(ga, gb), P.matmult(oa, ob))
+    a, b = rng.uniform(-1, 1, size=(h, tt)), rng.uniform(-1, 1, size=(tt, w))
+    (ga, oa), (gb, ob) = both(engines, a, T.D), both(engines, b, T.D)
+    g, wnt = P.matmult(ga, gb).to_numpy(), P.matmult(oa, ob).to_numpy()
+    bound = 2 * tt * np.finfo(np.float64).eps * (np.abs(a) @ np.abs(b))
+    assert np.all(np.abs(g - wnt) <= bound)
