@@ -163,6 +163,16 @@ PDLB200_API void  *pdlb200_host_alloc(size_t nbytes);
 PDLB200_API void   pdlb200_host_free(void *p);
 PDLB200_API int    pdlb200_memcpy_h2d(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);
 PDLB200_API int    pdlb200_memcpy_d2h(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);
+/* Unified (CUDA managed) memory: what the XS shim backs ndarray data with, so that the
+ * UNMODIFIED reference core can keep dereferencing pdl->data on the host while kernels use the
+ * same pointer; pages migrate on demand in both directions (= lazy host sync, done by the
+ * driver), and chained device ops never cross PCIe.  See perl/PDL-B200/B200.xs. */
+PDLB200_API void  *pdlb200_managed_alloc(size_t nbytes);
+PDLB200_API void   pdlb200_managed_free(void *p);
+/* 0 = plain host memory, 1 = device memory, 2 = managed, 3 = pinned host (device-visible) */
+PDLB200_API int    pdlb200_ptr_kind(const void *p);
+/* Migrate a managed range towards the device (to_device != 0) or the host ahead of use. */
+PDLB200_API int    pdlb200_prefetch(void *p, size_t nbytes, int to_device, void *stream, char *err, size_t errlen);
 /* Number of kernels this library has launched in this process (bench "gpu_launches"). */
 PDLB200_API uint64_t pdlb200_launch_count(void);
 /* Name of the kernel variant chosen by the most recent launch on this thread (introspection,

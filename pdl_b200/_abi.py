@@ -67,7 +67,8 @@ SYMBOLS = [
     "pdlb200_buf_upload", "pdlb200_buf_download", "pdlb200_buf_device_dirty",
     "pdlb200_abi_version", "pdlb200_device_count", "pdlb200_set_device", "pdlb200_sm_count",
     "pdlb200_sync", "pdlb200_host_alloc", "pdlb200_host_free", "pdlb200_memcpy_h2d",
-    "pdlb200_memcpy_d2h", "pdlb200_launch_count", "pdlb200_last_kernel", "pdlb200_op_name",
+    "pdlb200_memcpy_d2h", "pdlb200_managed_alloc", "pdlb200_managed_free", "pdlb200_ptr_kind",
+    "pdlb200_prefetch", "pdlb200_launch_count", "pdlb200_last_kernel", "pdlb200_op_name",
     "pdlb200_type_size",
 ]
 
@@ -125,6 +126,14 @@ def load():
         f = getattr(lib, name)
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p] + errargs
         f.restype = C.c_int
+    lib.pdlb200_managed_alloc.argtypes = [C.c_size_t]
+    lib.pdlb200_managed_alloc.restype = C.c_void_p
+    lib.pdlb200_managed_free.argtypes = [C.c_void_p]
+    lib.pdlb200_managed_free.restype = None
+    lib.pdlb200_ptr_kind.argtypes = [C.c_void_p]
+    lib.pdlb200_ptr_kind.restype = C.c_int
+    lib.pdlb200_prefetch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p] + errargs
+    lib.pdlb200_prefetch.restype = C.c_int
     lib.pdlb200_launch_count.restype = C.c_uint64
     lib.pdlb200_last_kernel.restype = C.c_char_p
     lib.pdlb200_op_name.argtypes = [C.c_int]

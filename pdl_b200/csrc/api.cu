@@ -195,6 +195,16 @@ int pdlb200_buf_new(size_t nbytes, pdlb200_buf **out, char *err, size_t errlen) 
   if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_buf_new: no CUDA device available");
   pdlb200_buf *b = new pdlb200_buf{nullptr, nbytes, 0, 0};
   cudaGetDevice(&b->device);
+  static bool pool_ready[16] = {false};
+  if (b->device >= 0 && b->device < 16 && !pool_ready[b->device]) {
+    // keep freed blocks in the pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, b->device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_ready[b->device] = true;
+  }
   if (nbytes) {
     // Stream-ordered pool: freed blocks are reused without returning to the driver, and there
     // is no zero-fill (the reference's memset in pdl_allocdata is ~75% of its config-1 time).
@@ -230,6 +240,33 @@ int pdlb200_buf_download(pdlb200_buf *b, void *host, size_t nbytes, int force, v
   if (nbytes) PDLB200_CUDA_OK(cudaMemcpyAsync(host, b->dev, nbytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream), E);
   PDLB200_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream), E);
   b->dev_dirty = 0;
+  return PDLB200_OK;
+}
+
+void *pdlb200_managed_alloc(size_t nbytes) {
+  if (probe_devices() <= 0) return nullptr;
+  void *p = nullptr;
+  if (cudaMallocManaged(&p, nbytes ? nbytes : 1, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pdlb200_managed_free(void *p) { if (p) cudaFree(p); }
+int pdlb200_ptr_kind(const void *p) {
+  if (!p || probe_devices() <= 0) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  switch (a.type) {
+    case cudaMemoryTypeDevice: return 1;
+    case cudaMemoryTypeManaged: return 2;
+    case cudaMemoryTypeHost: return 3;
+    default: return 0;
+  }
+}
+int pdlb200_prefetch(void *p, size_t nbytes, int to_device, void *stream, char *err, size_t errlen) {
+  Err E{err, errlen};
+  if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_prefetch: no CUDA device available");
+  int dev = 0;
+  PDLB200_CUDA_OK(cudaGetDevice(&dev), E);
+  PDLB200_CUDA_OK(cudaMemPrefetchAsync(p, nbytes, to_device ? dev : cudaCpuDeviceId, (cudaStream_t)stream), E);
   return PDLB200_OK;
 }
 

@@ -47,7 +47,8 @@ template <class T> __host__ __device__ __forceinline__ T from_bits(uint64_t bits
 }
 // PDL_ISBAD2 (lib/PDL/Core/pdl.h.PL:261-262)
 template <class T> __device__ __forceinline__ bool is_bad(T v, T badval, bool badnan) {
-  return badnan ? t_isnan(v) : (v == badval);
+  if constexpr (tt<T>::is_int) return v == badval;   // PDL_ISNAN_<int type> is constant 0
+  else return badnan ? t_isnan(v) : (v == badval);
 }
 
 // NaN results the way the reference's x86-64 SSE code produces them (IEEE 754 leaves the bits

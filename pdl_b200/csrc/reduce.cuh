@@ -217,17 +217,20 @@ template <class T, int KIND> struct RBits {
 };
 
 // ---- row walk -------------------------------------------------------------------
-template <class R, class T, bool BAD>
-__device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad, bool abadnan) {
-  if constexpr (BAD) { if (is_bad(v, abad, abadnan)) return; }
+// BADK: 0 = no BAD test (good-mode code path), 1 = BAD iff v == badvalue, 2 = BAD iff v is NaN
+// (per-ndarray NaN badvalue).  Hoisted to a template so the hot loop pays one compare at most.
+template <class R, class T, int BADK>
+__device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad) {
+  if constexpr (BADK == 1) { if (v == abad) return; }
+  if constexpr (BADK == 2) { if (t_isnan(v)) return; }
   R::lpush(loc, v, rel);
 }
 
 // Accumulate elements [lo, hi) of one row (hi - lo < 2^31); `lane` of `width` cooperating threads.
 // Each thread visits its elements in increasing index order.
-template <class R, class T, bool BAD>
-__device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64_t lo, int64_t hi, int64_t inc,
-                                       int lane, int width, T abad, bool abadnan) {
+template <class R, class T, int BADK>
+__device__ __forceinline__ void rd_row_k(typename R::Loc &loc, const T *row, int64_t lo, int64_t hi, int64_t inc,
+                                         int lane, int width, T abad) {
   constexpr int VEC = 16 / sizeof(T);
   const T *base = row + lo * inc;         // element `rel` lives at base[rel * inc]
   const int32_t len = (int32_t)(hi - lo);
@@ -236,7 +239,7 @@ __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64
     const uintptr_t addr = (uintptr_t)base;
     int32_t head = (int32_t)(((16 - (addr & 15)) & 15) / sizeof(T));
     if (head > len) head = len;
-    for (int32_t i = lane; i < head; i += width) rd_push<R, T, BAD>(loc, base[i], i, abad, abadnan);
+    for (int32_t i = lane; i < head; i += width) rd_push<R, T, BADK>(loc, base[i], i, abad);
     const int32_t nv = (len - head) / VEC;
     const uint4 *vp = reinterpret_cast<const uint4 *>(base + head);
     int32_t j = lane;
@@ -248,16 +251,16 @@ __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64
       for (int u = 0; u < RD_UNROLL; u++) {
         const int32_t e0 = head + (j + u * width) * VEC;
 #pragma unroll
-        for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(loc, r[u].e[k], e0 + k, abad, abadnan);
+        for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r[u].e[k], e0 + k, abad);
       }
     }
     for (; j < nv; j += width) {
       Pack<T> r; r.q = vp[j];
       const int32_t e0 = head + j * VEC;
 #pragma unroll
-      for (int k = 0; k < VEC; k++) rd_push<R, T, BAD>(loc, r.e[k], e0 + k, abad, abadnan);
+      for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r.e[k], e0 + k, abad);
     }
-    for (int32_t i = head + nv * VEC + lane; i < len; i += width) rd_push<R, T, BAD>(loc, base[i], i, abad, abadnan);
+    for (int32_t i = head + nv * VEC + lane; i < len; i += width) rd_push<R, T, BADK>(loc, base[i], i, abad);
   } else {
     int32_t i = lane;
     for (; i + (RD_UNROLL - 1) * width < len; i += RD_UNROLL * width) {
@@ -265,10 +268,19 @@ __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64
 #pragma unroll
       for (int u = 0; u < RD_UNROLL; u++) v[u] = base[(int64_t)(i + u * width) * inc];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) rd_push<R, T, BAD>(loc, v[u], i + u * width, abad, abadnan);
+      for (int u = 0; u < RD_UNROLL; u++) rd_push<R, T, BADK>(loc, v[u], i + u * width, abad);
     }
-    for (; i < len; i += width) rd_push<R, T, BAD>(loc, base[(int64_t)i * inc], i, abad, abadnan);
+    for (; i < len; i += width) rd_push<R, T, BADK>(loc, base[(int64_t)i * inc], i, abad);
   }
+}
+
+template <class R, class T, bool BAD>
+__device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64_t lo, int64_t hi, int64_t inc,
+                                       int lane, int width, T abad, bool abadnan) {
+  if constexpr (!BAD) rd_row_k<R, T, 0>(loc, row, lo, hi, inc, lane, width, abad);
+  else if constexpr (tt<T>::is_int) rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad);
+  else { if (abadnan) rd_row_k<R, T, 2>(loc, row, lo, hi, inc, lane, width, abad);
+         else rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad); }
 }
 
 __device__ __forceinline__ void rd_row_offsets(const RdPlan &p, int64_t row, int64_t &oa, int64_t &ob) {

@@ -216,7 +216,26 @@ def _check_output_dims(p: PDL, realdims: int, bc: Broadcast, opname: str, pname:
 
 # ---- the descriptor ---------------------------------------------------------------------------
 
+class Prepared:
+    """A transformation whose descriptor is already filled in: calling it is ONE C-ABI call.
+    The cached-descriptor fast path for repeated shapes (SURVEY.md §7 "launch-latency floor"):
+    type selection, broadcast merging and output creation were done once by prepare_op()."""
+
+    __slots__ = ("engine", "trans", "outputs", "_keep")
+
+    def __init__(self, engine, trans, outputs, keep):
+        self.engine, self.trans, self.outputs, self._keep = engine, trans, outputs, keep
+
+    def __call__(self):
+        self.engine.readdata(self.trans)
+        return self.outputs
+
+
 def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> None:
+    pdls[0].engine.readdata(_build_trans(spec, transtype, pdls, bc, named, bval))
+
+
+def _build_trans(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> _abi.Trans:
     if len(bc.dims) > _abi.MAXDIMS:
         raise PDLError(f"PDL::{spec.name}: more than {_abi.MAXDIMS} broadcast dims")
     tr = _abi.Trans()
@@ -237,7 +256,7 @@ def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict
         par.type = p.datatype
         par.badval = p.badvalue_bits()
         par.flags = (_abi.PAR_BADFLAG if p.badflag else 0) | (_abi.PAR_BADNAN if p.badvalue_isnan() else 0)
-    pdls[0].engine.readdata(tr)
+    return tr
 
 
 def _real_inc(p: PDL, j: int) -> int:
@@ -245,7 +264,13 @@ def _real_inc(p: PDL, j: int) -> int:
     return 0 if (p.ndims <= j or p.dims[j] <= 1) else p.dimincs[j]
 
 
-def run_op(name: str, inputs: list, outputs: list | None = None) -> list:
+def prepare_op(name: str, inputs: list, outputs: list | None = None) -> Prepared:
+    """Like run_op, but returns a Prepared instead of launching.  Only for calls that need no
+    type conversion of inputs or outputs (a single readdata)."""
+    return run_op(name, inputs, outputs, _prepare=True)
+
+
+def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False):
     """pdl_run_<name>(inputs..., outputs...).  `outputs` entries may be None (null ndarray:
     created with the broadcast dims).  Returns the output ndarrays."""
     spec = SPECS[name]
@@ -267,6 +292,8 @@ def run_op(name: str, inputs: list, outputs: list | None = None) -> list:
         raise PDLError(f"PDL::{name}: type {T.NAMES[transtype]} has no device representation "
                        "(long double / complex are outside the device type matrix)")
     # inputs to the type the loop is instantiated for (converttypei -> device convert kernel)
+    if _prepare and any(x.datatype != par_type(par, transtype) for x, par in zip(ins, in_pars)):
+        raise PDLError(f"PDL::{name}: prepare_op needs inputs already in the operation's type")
     ins = [x if x.datatype == par_type(par, transtype) else convert_type(x, par_type(par, transtype))
            for x, par in zip(ins, in_pars)]
     bval = any(x.badflag for x in ins)
@@ -335,6 +362,10 @@ def run_op(name: str, inputs: list, outputs: list | None = None) -> list:
         named = {"ind": [ind["t"], ind["h"], ind["w"]],
                  "rinc": [_real_inc(a, 0), _real_inc(a, 1), _real_inc(b, 0), _real_inc(b, 1),
                           _real_inc(c, 0), _real_inc(c, 1)]}
+    if _prepare:
+        if temps:
+            raise PDLError(f"PDL::{name}: prepare_op needs outputs already in the operation's type")
+        return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder)
     _launch(spec, transtype, placeholder, bc, named, bval)
 
     for target, o in temps:

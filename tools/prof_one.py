@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Launch ONE op of the bench workload a few times (for `ncu --set full -k regex:...`).
+Usage: python tools/prof_one.py {sumover|average|minimum|plus|mult_cfg3|matmult} [reps]"""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+import pdl_b200 as P  # noqa: E402
+from pdl_b200 import types as T  # noqa: E402
+
+op = sys.argv[1] if len(sys.argv) > 1 else "minimum"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+eng = P.CudaEngine(0)
+dev = torch.device("cuda", 0)
+
+
+def wrap(t, typ, dims):
+    return P.PDL(eng, eng.wrap(t.data_ptr(), t.numel() * t.element_size(), t), typ, dims)
+
+
+if op in ("sumover", "average", "minimum", "maximum"):
+    rows = 65536
+    x = bench.generate_device(torch, 0, rows, dev)
+    a = wrap(x, T.F, [bench.N_DIM, rows]).set_badflag(True)
+    out = P.PDL.empty(T.F, [rows], eng)
+    f = P.prepare_op(op, [a], [out])
+elif op == "plus":
+    n = 2048 * 2048
+    y, c, o = (torch.rand(n, dtype=torch.float64, device=dev) for _ in range(3))
+    f = P.prepare_op("plus", [wrap(y, T.D, [2048, 2048]), wrap(c, T.D, [2048, 2048])], [wrap(o, T.D, [2048, 2048])])
+elif op == "mult_cfg3":
+    N = 32768
+    b1, b2 = torch.rand(2 * N, dtype=torch.float64, device=dev), torch.rand(2 * N, dtype=torch.float64, device=dev)
+    pr = torch.empty(N * N, dtype=torch.float64, device=dev)
+    f = P.prepare_op("mult", [wrap(b1, T.D, [2 * N]).slice("0:-1:2").dummy(1, 1),
+                              wrap(b2, T.D, [2 * N]).slice("0:-1:2").dummy(0, 1)], [wrap(pr, T.D, [N, N])])
+elif op == "matmult":
+    n = 4096
+    A, B, Cc = (torch.rand((n, n), dtype=torch.float64, device=dev) for _ in range(3))
+    f = P.prepare_op("matmult", [wrap(A, T.D, [n, n]), wrap(B, T.D, [n, n])], [wrap(Cc, T.D, [n, n])])
+else:
+    raise SystemExit(f"unknown op {op}")
+for _ in range(reps):
+    f()
+torch.cuda.synchronize()
+print("done", op, eng.last_kernel())
