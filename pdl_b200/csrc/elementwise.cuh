@@ -24,7 +24,9 @@ struct EwPlan {
   int64_t st[3][MAXD];         // element strides per collapsed dim
   int64_t dims[MAXD];
   int64_t n_units;             // vpr * prod(dims[1..])
-  int64_t vpr;                 // vectors per row = ceil(dims[0]/VEC)
+  int64_t vpr;                 // vectors per row = ceil(dims[0]/VEC)   (tile kernel: tiles per row)
+  int64_t ipr;                 // tile kernel: work items per row
+  int grp;                     // tile kernel: consecutive tiles of one row per work item
   uint64_t bad[3];             // badvalue bits per operand
   int nd;
   int badnan[3];
@@ -141,9 +143,9 @@ ew_kernel(const __grid_constant__ EwPlan p) {
 
 // ---- tile kernel: the fast path --------------------------------------------------------------
 // A tile = TILE = EW_THREADS*UNROLL*VEC consecutive positions of collapsed dim 0 inside ONE outer
-// row.  The outer-index decode (div/mod over dims[1..]) and the per-operand row offsets are computed
-// once per tile; inside the tile every unit is base + constant stride, so the per-16-byte cost is a
-// handful of integer instructions.  Stride-0 (dummy-dim) operands are loaded once per tile.
+// row; a work item = up to `grp` consecutive tiles of one row.  The outer-index decode (div/mod
+// over dims[1..]) and the per-operand row offsets are computed once per work item; inside it every
+// unit is base + constant stride, so the per-16-byte cost is a handful of integer instructions.
 // Used when dim 0 is long enough to fill tiles (always for fully collapsed contiguous ndarrays).
 template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
 __global__ void __launch_bounds__(EW_THREADS)
@@ -153,62 +155,64 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
   const TI abad = from_bits<TI>(p.bad[0]);
   const TI bbad = from_bits<TI>(p.bad[NIN > 1 ? 1 : 0]);
   const TO cbad = from_bits<TO>(p.bad[NIN]);
-  const int64_t tpr = p.vpr;       // tiles per row (host stores it in vpr for this kernel)
-  const int64_t ntiles = p.n_units;
+  const int64_t tpr = p.vpr, ipr = p.ipr, nitems = p.n_units;
   const int64_t sa0 = p.st[0][0], sb0 = (NIN > 1) ? p.st[1][0] : 0, sc0 = p.st[NIN][0];
+  const int64_t ja = (int64_t)EW_THREADS * VEC * sa0, jb = (int64_t)EW_THREADS * VEC * sb0, jc = (int64_t)EW_THREADS * VEC * sc0;
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    int64_t row, seg;
-    if (p.nd == 1) { row = 0; seg = tile; }
-    else if ((uint64_t)ntiles <= 0xffffffffull) { const uint32_t r32 = (uint32_t)tile / (uint32_t)tpr; row = r32; seg = (uint32_t)tile - r32 * (uint32_t)tpr; }
-    else { row = tile / tpr; seg = tile - row * tpr; }
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    int64_t row = 0, it = item;
     int64_t oa = 0, ob = 0, oc = 0;
-    for (int d = 1; d < p.nd; d++) {
-      int64_t q, i;
-      if (d == p.nd - 1) { i = row; q = 0; }
-      else if ((uint64_t)row <= 0xffffffffull && (uint64_t)p.dims[d] <= 0xffffffffull) {
-        const uint32_t q32 = (uint32_t)row / (uint32_t)p.dims[d]; q = q32; i = (uint32_t)row - q32 * (uint32_t)p.dims[d];
-      } else { q = row / p.dims[d]; i = row - q * p.dims[d]; }
-      oa += i * p.st[0][d];
-      if (NIN > 1) ob += i * p.st[1][d];
-      oc += i * p.st[NIN][d];
-      row = q;
+    if (p.nd > 1) {
+      row = item / ipr; it = item - row * ipr;
+      int64_t r = row;
+      for (int d = 1; d < p.nd; d++) {
+        const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d];
+        const int64_t i = r - q * p.dims[d];
+        oa += i * p.st[0][d];
+        if (NIN > 1) ob += i * p.st[1][d];
+        oc += i * p.st[NIN][d];
+        r = q;
+      }
     }
-    const int64_t i_first = seg * TILE + (int64_t)threadIdx.x * VEC;  // this thread's first position in the row
+    const int64_t seg0 = it * p.grp;
+    const int64_t seg1 = (seg0 + p.grp < tpr) ? seg0 + p.grp : tpr;
+    int64_t i_first = seg0 * TILE + (int64_t)threadIdx.x * VEC;   // this thread's first position in the row
     const TI *pa = reinterpret_cast<const TI *>(p.ptr[0]) + oa + i_first * sa0;
     const TI *pb = reinterpret_cast<const TI *>(p.ptr[NIN > 1 ? 1 : 0]) + ob + i_first * sb0;
     TO *pc = reinterpret_cast<TO *>(p.ptr[NIN]) + oc + i_first * sc0;
-    const int64_t left0 = p.dims[0] - i_first;
 
-    Pack<TI> ra[UNROLL], rb[UNROLL];
+    for (int64_t seg = seg0; seg < seg1; seg++, i_first += TILE, pa += UNROLL * ja, pb += UNROLL * jb, pc += UNROLL * jc) {
+      const int64_t left0 = p.dims[0] - i_first;
+      Pack<TI> ra[UNROLL], rb[UNROLL];
 #pragma unroll
-    for (int j = 0; j < UNROLL; j++) {
-      const int64_t left = left0 - (int64_t)j * EW_THREADS * VEC;
-      if (left > 0) {
-        const int cnt = left < VEC ? (int)left : VEC;
-        ew_load<TI, VEC>(ra[j], reinterpret_cast<const char *>(pa + (int64_t)j * EW_THREADS * VEC * sa0), 0, sa0, p.vec[0], cnt);
-        if (NIN > 1) ew_load<TI, VEC>(rb[j], reinterpret_cast<const char *>(pb + (int64_t)j * EW_THREADS * VEC * sb0), 0, sb0, p.vec[1], cnt);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < UNROLL; j++) {
-      const int64_t left = left0 - (int64_t)j * EW_THREADS * VEC;
-      if (left > 0) {
-        const int cnt = left < VEC ? (int)left : VEC;
-        Pack<TO> rc;
-#pragma unroll
-        for (int k = 0; k < VEC; k++) {
-          const TI a = ra[j].e[k];
-          const TI b = (NIN > 1) ? rb[j].e[k] : TI(0);
-          bool bad = false;
-          if constexpr (BAD) {
-            bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
-            if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
-          }
-          const TO r = Op::template f<TI, TO>(a, b);
-          rc.e[k] = bad ? cbad : r;
+      for (int j = 0; j < UNROLL; j++) {
+        const int64_t left = left0 - (int64_t)j * EW_THREADS * VEC;
+        if (left > 0) {
+          const int cnt = left < VEC ? (int)left : VEC;
+          ew_load<TI, VEC>(ra[j], reinterpret_cast<const char *>(pa + j * ja), 0, sa0, p.vec[0], cnt);
+          if (NIN > 1) ew_load<TI, VEC>(rb[j], reinterpret_cast<const char *>(pb + j * jb), 0, sb0, p.vec[1], cnt);
         }
-        ew_store<TO, VEC>(rc, reinterpret_cast<char *>(pc + (int64_t)j * EW_THREADS * VEC * sc0), 0, sc0, p.vec[NIN], cnt);
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) {
+        const int64_t left = left0 - (int64_t)j * EW_THREADS * VEC;
+        if (left > 0) {
+          const int cnt = left < VEC ? (int)left : VEC;
+          Pack<TO> rc;
+#pragma unroll
+          for (int k = 0; k < VEC; k++) {
+            const TI a = ra[j].e[k];
+            const TI b = (NIN > 1) ? rb[j].e[k] : TI(0);
+            bool bad = false;
+            if constexpr (BAD) {
+              bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
+              if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
+            }
+            const TO r = Op::template f<TI, TO>(a, b);
+            rc.e[k] = bad ? cbad : r;
+          }
+          ew_store<TO, VEC>(rc, reinterpret_cast<char *>(pc + j * jc), 0, sc0, p.vec[NIN], cnt);
+        }
       }
     }
   }
@@ -230,10 +234,18 @@ int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *
   constexpr int TU = 4;                                    // units per thread per tile
   constexpr int64_t TILE = (int64_t)EW_THREADS * TU * VEC;
   if (p.nd == 1 || p.dims[0] >= TILE / 2) {
-    // tile kernel: re-purpose vpr/n_units as tiles-per-row / number of tiles
+    // tile kernel: re-purpose vpr/n_units as tiles-per-row / number of work items.  A work item is
+    // `grp` consecutive tiles of one row: 1 for small problems (keeps every SM busy), up to 8 for
+    // big ones (amortises the per-item index decode).
     const int64_t tpr = (p.dims[0] + TILE - 1) / TILE;
     const int64_t rows = p.n_units / p.vpr;
-    p.vpr = tpr; p.n_units = tpr * rows;
+    int64_t grp = (tpr * rows) / ((int64_t)sm_count() * 16);
+    if (grp > 8) grp = 8;
+    if (grp > tpr) grp = tpr;
+    if (grp < 1) grp = 1;
+    p.grp = (int)grp;
+    p.ipr = (tpr + grp - 1) / grp;
+    p.vpr = tpr; p.n_units = p.ipr * rows;
     const int64_t cap = (int64_t)sm_count() * 32;
     const int grid = (int)(p.n_units < cap ? p.n_units : cap);
     if (t->bvalflag) ew_tile_kernel<Op, TI, TO, true, NIN, TU><<<grid, EW_THREADS, 0, s>>>(p);

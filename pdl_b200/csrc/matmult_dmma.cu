@@ -38,8 +38,17 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// D(16x8) += A(16x8) * B(8x8).  a0:(g,t) a1:(g+8,t) a2:(g,t+4) a3:(g+8,t+4); b0:(k=t,n=g) b1:(k=t+4,n=g);
+// c0,c1:(g, 2t+{0,1}) c2,c3:(g+8, 2t+{0,1})
+__device__ __forceinline__ void dmma1688(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+               : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+
 // ALIGNED16: every row start of A, B (and the k/w offsets used) is 16-byte aligned -> 16-byte LDGSTS
-template <bool ALIGNED16>
+// SHAPE: 0 = m8n8k4 instructions, 1 = m16n8k8 (4x fewer, 4x larger tensor-pipe issues)
+template <bool ALIGNED16, int SHAPE>
 __global__ void __launch_bounds__(256, 1)
 mm_dmma_kernel(const __grid_constant__ MmPlan p) {
   extern __shared__ __align__(16) double smem[];
@@ -114,7 +123,9 @@ mm_dmma_kernel(const __grid_constant__ MmPlan p) {
     }
   };
 
-  double acc[8][4][2];   // [m8 tile][n8 tile][col pair]
+  // accumulators: SHAPE 0: acc[i][j][0..1] = C[8i+g][8j+2t+{0,1}];  SHAPE 1 groups m8 tiles in pairs:
+  // acc16[i][j][0..3] = C[16i+g][..], C[16i+g+8][..]
+  double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -136,17 +147,44 @@ mm_dmma_kernel(const __grid_constant__ MmPlan p) {
     }
     const double *tA = sA + (kt % DM_STAGES) * DM_A_STAGE + (wm * 64) * DM_LDA;
     const double *tB = sB + (kt % DM_STAGES) * DM_B_STAGE + wn * 32;
+    if (SHAPE == 0) {
 #pragma unroll
-    for (int ks = 0; ks < DM_BK; ks += 4) {
-      double af[8], bf[4];
+      for (int ks = 0; ks < DM_BK; ks += 4) {
+        double af[8], bf[4];
 #pragma unroll
-      for (int i = 0; i < 8; i++) af[i] = tA[(i * 8 + g) * DM_LDA + ks + t4];
+        for (int i = 0; i < 8; i++) af[i] = tA[(i * 8 + g) * DM_LDA + ks + t4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) bf[j] = tB[(ks + t4) * DM_LDB + j * 8 + g];
+        for (int j = 0; j < 4; j++) bf[j] = tB[(ks + t4) * DM_LDB + j * 8 + g];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    } else {
+#pragma unroll
+      for (int ks = 0; ks < DM_BK; ks += 8) {
+        double af[4][4], bf[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          af[i][0] = tA[(i * 16 + g) * DM_LDA + ks + t4];
+          af[i][1] = tA[(i * 16 + g + 8) * DM_LDA + ks + t4];
+          af[i][2] = tA[(i * 16 + g) * DM_LDA + ks + t4 + 4];
+          af[i][3] = tA[(i * 16 + g + 8) * DM_LDA + ks + t4 + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          bf[j][0] = tB[(ks + t4) * DM_LDB + j * 8 + g];
+          bf[j][1] = tB[(ks + t4 + 4) * DM_LDB + j * 8 + g];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            double c4[4] = {acc[2 * i][j][0], acc[2 * i][j][1], acc[2 * i + 1][j][0], acc[2 * i + 1][j][1]};
+            dmma1688(c4, af[i], bf[j]);
+            acc[2 * i][j][0] = c4[0]; acc[2 * i][j][1] = c4[1]; acc[2 * i + 1][j][0] = c4[2]; acc[2 * i + 1][j][1] = c4[3];
+          }
+      }
     }
   }
   cp_wait<0>();
@@ -172,25 +210,34 @@ mm_dmma_kernel(const __grid_constant__ MmPlan p) {
   }
 }
 
+template <bool ALIGNED16, int SHAPE>
+static int dmma_go(const MmPlan &p, dim3 grid, cudaStream_t s, const Err &E) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_kernel<ALIGNED16, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM), E);
+    attr_set = true;
+  }
+  mm_dmma_kernel<ALIGNED16, SHAPE><<<grid, 256, DM_SMEM, s>>>(p);
+  return PDLB200_OK;
+}
+
 int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
   // eligibility: unit stride along t in a and along w in b (PDL's default physical layout)
   if (p.T == 0) return PDLB200_EUNSUPPORTED;
   if (!((p.iat == 1 || p.T == 1) && (p.ibw == 1 || p.W == 1))) return PDLB200_EUNSUPPORTED;
   if (p.H * p.W < 64 * 64) return PDLB200_EUNSUPPORTED;   // tiny products: the exact kernel is as fast and bit-exact
-  static bool attr_set[2] = {false, false};
   bool aligned = ((((uintptr_t)p.a) | ((uintptr_t)p.b)) & 15) == 0 && (p.iah % 2 == 0) && (p.ibt % 2 == 0) &&
                  p.iat == 1 && p.ibw == 1;
   for (int d = 0; d < p.nd && aligned; d++) if ((p.sa[d] % 2) || (p.sb[d] % 2)) aligned = false;
   dim3 grid((unsigned)((p.W + DM_BN - 1) / DM_BN), (unsigned)((p.H + DM_BM - 1) / DM_BM), (unsigned)p.nbatch);
   cudaStream_t s = (cudaStream_t)t->stream;
-  if (aligned) {
-    if (!attr_set[0]) { PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM), E); attr_set[0] = true; }
-    mm_dmma_kernel<true><<<grid, 256, DM_SMEM, s>>>(p);
-  } else {
-    if (!attr_set[1]) { PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DM_SMEM), E); attr_set[1] = true; }
-    mm_dmma_kernel<false><<<grid, 256, DM_SMEM, s>>>(p);
-  }
-  note_launch(aligned ? "matmult_dmma_v16" : "matmult_dmma_v8");
+  const char *sh = getenv("PDLB200_DMMA_SHAPE");
+  const int shape = (sh && !strcmp(sh, "884")) ? 0 : 1;
+  int rc;
+  if (aligned) rc = shape ? dmma_go<true, 1>(p, grid, s, E) : dmma_go<true, 0>(p, grid, s, E);
+  else         rc = shape ? dmma_go<false, 1>(p, grid, s, E) : dmma_go<false, 0>(p, grid, s, E);
+  if (rc) return rc;
+  note_launch(aligned ? (shape ? "matmult_dmma1688_v16" : "matmult_dmma884_v16") : (shape ? "matmult_dmma1688_v8" : "matmult_dmma884_v8"));
   PDLB200_CUDA_OK(cudaGetLastError(), E);
   return PDLB200_OK;
 }
