@@ -66,6 +66,8 @@ enum {
   /* more a(n); [o]b() reductions, lib/PDL/Ufunc.pd:143-187 */
   PDLB200_OP_ANDOVER = 40, PDLB200_OP_OROVER, PDLB200_OP_BANDOVER, PDLB200_OP_BOROVER,
   PDLB200_OP_ZCOVER, PDLB200_OP_XOROVER, PDLB200_OP_BXOROVER,
+  /* lib/PDL/Bad.pd:418-480 : a(n); indx [o]b() — the good/bad counts a sharded average needs */
+  PDLB200_OP_NBADOVER = 47, PDLB200_OP_NGOODOVER,
   /* scans, lib/PDL/Ufunc.pd:120-141 : a(n); [o]b(n) */
   PDLB200_OP_CUMUSUMOVER = 50, PDLB200_OP_CUMUPRODOVER, PDLB200_OP_DCUMUSUMOVER, PDLB200_OP_DCUMUPRODOVER,
   /* matmult, lib/PDL/Primitive.pd:191-264 : a(t,h); b(w,t); [o]c(w,h) */

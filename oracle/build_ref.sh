@@ -35,6 +35,12 @@ cp lib/PDL/Ops-pp-plus.c lib/PDL/Ops-pp-divide.c lib/PDL/Ops-pp-modulo.c lib/PDL
    lib/PDL/Ufunc-pp-sumover.c lib/PDL/Ufunc-pp-average.c lib/PDL/Ufunc-pp-minimum.c \
    lib/PDL/Ufunc-pp-prodover.c lib/PDL/Ufunc-pp-maximum_ind.c \
    lib/PDL/Primitive-pp-matmult.c "$OUT/gen/" 2>/dev/null || true
+# the reference's own hot-path tests, so they can be re-run on the GPU box with the shim attached
+# (oracle/_ref is git-ignored: nothing from the reference enters the repository history)
+mkdir -p "$OUT/t"
+for f in ops.t ops-bitwise.t ufunc.t bad.t primitive-matmult.t thread.t slice.t core.t clump.t reduce.t; do
+  cp "t/$f" "$OUT/t/" 2>/dev/null || true
+done
 find "$OUT" -name '*.pod' -delete
 perl -I"$OUT/blib/lib" -I"$OUT/blib/arch" -MPDL::LiteF -e \
   'print "oracle/_ref: PDL $PDL::VERSION pthreads=", PDL::Core::pthreads_enabled(), " cpus=", PDL::Core::online_cpus(), "\n"'

@@ -55,7 +55,7 @@ OPS = {
     "average": 34, "daverage": 35, "minimum": 36, "maximum": 37,
     "minimum_ind": 38, "maximum_ind": 39,
     "andover": 40, "orover": 41, "bandover": 42, "borover": 43,
-    "zcover": 44, "xorover": 45, "bxorover": 46,
+    "zcover": 44, "xorover": 45, "bxorover": 46, "nbadover": 47, "ngoodover": 48,
     "cumusumover": 50, "cumuprodover": 51, "dcumusumover": 52, "dcumuprodover": 53,
     "matmult": 60, "converttype": 61,
 }

@@ -74,6 +74,7 @@ static void init_names() {
   N(PDLB200_OP_MAXIMUM_IND, "maximum_ind") N(PDLB200_OP_ANDOVER, "andover") N(PDLB200_OP_OROVER, "orover")
   N(PDLB200_OP_BANDOVER, "bandover") N(PDLB200_OP_BOROVER, "borover") N(PDLB200_OP_ZCOVER, "zcover")
   N(PDLB200_OP_XOROVER, "xorover") N(PDLB200_OP_BXOROVER, "bxorover")
+  N(PDLB200_OP_NBADOVER, "nbadover") N(PDLB200_OP_NGOODOVER, "ngoodover")
   N(PDLB200_OP_CUMUSUMOVER, "cumusumover") N(PDLB200_OP_CUMUPRODOVER, "cumuprodover")
   N(PDLB200_OP_DCUMUSUMOVER, "dcumusumover") N(PDLB200_OP_DCUMUPRODOVER, "dcumuprodover")
   N(PDLB200_OP_MATMULT, "matmult") N(PDLB200_OP_CONVERT, "converttype")
@@ -161,7 +162,7 @@ int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
   Err E{err, errlen};
   if (int rc = validate(t, E)) return rc;
   if (t->op >= PDLB200_OP_CUMUSUMOVER && t->op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
-  if (t->op >= PDLB200_OP_SUMOVER && t->op <= PDLB200_OP_BXOROVER) return launch_reduce(t, E);
+  if (t->op >= PDLB200_OP_SUMOVER && t->op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
 }
 int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
@@ -176,7 +177,7 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   const int op = t->op;
   if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT) return launch_elementwise(t, E);
   if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
-  if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_BXOROVER) return launch_reduce(t, E);
+  if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);
   return E.fail(PDLB200_EINVAL, "pdlb200: op %d has no launcher", op);
 }

@@ -216,6 +216,22 @@ template <class T, int KIND> struct RBits {
   }
 };
 
+// nbadover / ngoodover (lib/PDL/Bad.pd:418-480): counts, output indx.  Only good elements reach
+// lpush, so the accumulator counts those; nbad = n - ngood (good mode: nbad = 0, ngood = n).
+template <class T, bool GOOD> struct RCount {
+  static constexpr bool kPrefix = false;
+  struct Loc { int32_t cnt; };
+  struct Acc { int64_t cnt; };
+  static __device__ __forceinline__ Loc linit() { Loc x; x.cnt = 0; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T, int32_t) { x.cnt++; }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.cnt = l.cnt; return x; }
+  static __device__ __forceinline__ Acc init() { Acc x; x.cnt = 0; return x; }
+  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.cnt = l.cnt + r.cnt; return x; }
+  static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, int64_t *out) {
+    *out = GOOD ? x.cnt : (p.n - x.cnt);
+  }
+};
+
 // ---- row walk -------------------------------------------------------------------
 // BADK: 0 = no BAD test (good-mode code path), 1 = BAD iff v == badvalue, 2 = BAD iff v is NaN
 // (per-ndarray NaN badvalue).  Hoisted to a template so the hot loop pays one compare at most.

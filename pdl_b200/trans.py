@@ -86,6 +86,13 @@ SPECS = {s.name: s for s in [
     _rd("minimum_ind", _R, T.IND), _rd("maximum_ind", _R, T.IND),
     _rd("andover", _A), _rd("orover", _A), _rd("zcover", _A), _rd("xorover", _A),
     _rd("bandover", _I), _rd("borover", _I), _rd("bxorover", _I),
+    # lib/PDL/Bad.pd:418-480
+    _rd("nbadover", _A, T.IND), _rd("ngoodover", _A, T.IND),
+    # scans, lib/PDL/Ufunc.pd:120-141 : a(n); [o]b(n)
+    OpSpec("cumusumover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.L, tplus=True)], _A, "scan"),
+    OpSpec("cumuprodover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.L, tplus=True)], _A, "scan"),
+    OpSpec("dcumusumover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.D)], _R, "scan"),
+    OpSpec("dcumuprodover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.D)], _R, "scan"),
     # matmult, lib/PDL/Primitive.pd:191-195
     OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
 ]}
@@ -357,6 +364,9 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
         if ind["n"] == 0 and name in ("minimum", "maximum", "minimum_ind", "maximum_ind"):
             for o in placeholder[len(ins):]:
                 o.badflag = True
+    elif spec.kind == "scan":
+        a, b = placeholder
+        named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0)]}
     elif spec.kind == "matmult":
         a, b, c = placeholder
         named = {"ind": [ind["t"], ind["h"], ind["w"]],

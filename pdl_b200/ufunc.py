@@ -6,7 +6,8 @@ from .trans import run_op, as_pdl
 
 _REDUCERS = ["sumover", "prodover", "dsumover", "dprodover", "average", "daverage",
              "minimum", "maximum", "minimum_ind", "maximum_ind",
-             "andover", "orover", "zcover", "xorover", "bandover", "borover", "bxorover"]
+             "andover", "orover", "zcover", "xorover", "bandover", "borover", "bxorover",
+             "nbadover", "ngoodover", "cumusumover", "cumuprodover", "dcumusumover", "dcumuprodover"]
 
 
 def _mk(name):

@@ -104,7 +104,11 @@ static void *device_view(pdl *p, int is_output, staged_t *st, int *nst) {
   if ((size_t)owner->nbytes <= STAGE_MAX && g_stage_used + (size_t)owner->nbytes + 64 <= STAGE_BYTES) {
     int i;
     char *slot;
-    for (i = 0; i < *nst; i++) if (st[i].owner == owner) return st[i].slot;   /* aliasing parameters share a slot */
+    for (i = 0; i < *nst; i++)
+      if (st[i].owner == owner) {               /* aliasing parameters (inplace ops) share a slot */
+        if (is_output) st[i].nbytes = (size_t)owner->nbytes;
+        return st[i].slot;
+      }
     slot = g_stage + g_stage_used;
     g_stage_used += ((size_t)owner->nbytes + 63) & ~(size_t)63;
     memcpy(slot, owner->data, (size_t)owner->nbytes);

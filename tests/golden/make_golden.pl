@@ -290,6 +290,19 @@ for my $t (qw(float double)) {
   add_case("long-row-sumover-$t", [[mk($t,[5000,3],'small')]], {kind=>'reduce', op=>'sumover'}, 0);
   add_case("long-row-average-$t", [[mk($t,[5000,3],'small')]], {kind=>'reduce', op=>'average'}, 0);
 }
+# counts (Bad.pd:418-480) and scans (Ufunc.pd:120-141)
+for my $t (@TYPES) {
+  my $b = with_bad(mk($t,[11,3],'small'), 0, 5, 12, (map { 22 + $_ } 0..10));   # row 2 all BAD
+  for my $op (qw(nbadover ngoodover)) {
+    add_case("$op-$t", [[$b]], {kind=>'reduce', op=>$op});
+    add_case("$op-$t-noflag", [[mk($t,[7,2],'small')]], {kind=>'reduce', op=>$op});
+  }
+  for my $op (qw(cumusumover cumuprodover dcumusumover dcumuprodover)) {
+    add_case("$op-$t", [[mk($t,[9,3],'small')]], {kind=>'reduce', op=>$op}, $IS_INT{$t} ? undef : 0);
+    add_case("bad-$op-$t", [[$b]], {kind=>'reduce', op=>$op}, $IS_INT{$t} ? undef : 0);
+  }
+  add_case("cumusumover-$t-wrap-xchg", [[mk($t,[6,20],'mixed'), [['xchg',0,1]]]], {kind=>'reduce', op=>'cumusumover'});
+}
 flush_cases('reduce.json');
 
 # ---------------------------------------------------------------- matmult (Primitive.pd:191-264; t/primitive-matmult.t)
