@@ -5,9 +5,16 @@
 // FP64 tensor path on sm_100a is mma.sync (SASS: DMMA).  Roofline: FP64 tensor peak;
 // 2*T*H*W flop, minimum traffic 8*(H*T + T*W + H*W) bytes.
 //
-// CTA tile 128x128, BK = 16, 256 threads = 8 warps (2 x 4), warp tile 64x32, 4-stage
-// cp.async (LDGSTS) ring.  Shared-memory rows are padded (A: 20 doubles, B: 132 doubles) so
-// that the 64-bit fragment loads of a half-warp hit 16 distinct banks.
+// Default kernel (mm_dmma_ws_kernel): CTA tile 128x128, BK = 16, warp-specialised — 16 consumer
+// warps (4 x 4, warp tile 32x32: LDS.64 fragment loads + DMMA only) and 4 producer warps that issue
+// every cp.async (LDGSTS.128) of a 4-stage ring, handshaking through per-stage full/empty
+// mbarriers (cp.async.mbarrier.arrive.noinc on the producer side).  One producer warp could not
+// issue the 2048 16-byte copies of a stage fast enough (consumers sat 17% of the time in
+// try_wait, ncu SASS sampling); four do: 35.1 TFLOP/s at 8192^3 = 0.99 of cuBLAS DGEMM, 0.95 of the
+// 37.1 TFLOP/s DMMA issue peak measured with tools/ubench/dmma_rate.cu.
+// PDLB200_DMMA=sync selects the older 8-warp __syncthreads pipeline (31.2 TFLOP/s).
+// Shared-memory rows are padded (A: 20 doubles, B: 132 doubles) so that the 64-bit fragment
+// loads of a half-warp hit 16 distinct banks (ncu: no LDS conflicts).
 // The MMA adds with fused multiply-add, so results equal the reference's separate
 // multiply/add only within tolerance (bit-exact when every product and partial sum is exactly
 // representable; tests/test_gpu_parity.py pins both).
@@ -221,6 +228,196 @@ static int dmma_go(const MmPlan &p, dim3 grid, cudaStream_t s, const Err &E) {
   return PDLB200_OK;
 }
 
+// ---- warp-specialised variant ---------------------------------------------------------------
+// 8 consumer warps (LDS + DMMA only) + 1 producer warp (all cp.async for both operand tiles),
+// connected by per-stage full/empty mbarriers instead of a CTA-wide __syncthreads per k-tile:
+// the tensor pipe no longer idles while every warp recomputes load addresses after the barrier.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t *bar) {
+  // arrives (without bumping the expected count) once all of this thread's prior cp.async have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n"
+      :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+constexpr int WS_MAX_STAGES = 6;
+constexpr size_t ws_smem(int stages) { return (size_t)stages * (DM_A_STAGE + DM_B_STAGE) * sizeof(double) + 2 * WS_MAX_STAGES * sizeof(uint64_t); }
+
+// NCW consumer warps: 8 -> 2x4 warps of 64x32 tiles, 16 -> 4x4 warps of 32x32 tiles (more warps per
+// scheduler to cover the fixed DMMA issue latency)
+template <bool ALIGNED16, int NCW, int WS_STAGES, int NPW>
+__global__ void __launch_bounds__(NCW * 32 + NPW * 32, 1)
+mm_dmma_ws_kernel(const __grid_constant__ MmPlan p) {
+  constexpr int MT = (NCW == 8) ? 8 : 4;          // m8 tiles per warp
+  extern __shared__ __align__(16) double smem[];
+  double *sA = smem;
+  double *sB = smem + WS_STAGES * DM_A_STAGE;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + WS_STAGES * (DM_A_STAGE + DM_B_STAGE));
+  uint64_t *empty = full + WS_STAGES;
+
+  int64_t oa = 0, ob = 0, oc = 0;
+  {
+    int64_t row = blockIdx.z;
+    for (int d = 0; d < p.nd; d++) {
+      const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
+      const int64_t i = row - q * p.dims[d];
+      oa += i * p.sa[d]; ob += i * p.sb[d]; oc += i * p.sc[d];
+      row = q;
+    }
+  }
+  const double *A = reinterpret_cast<const double *>(p.a) + oa;
+  const double *B = reinterpret_cast<const double *>(p.b) + ob;
+  double *C = reinterpret_cast<double *>(p.c) + oc;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t h0 = (int64_t)blockIdx.y * DM_BM, w0 = (int64_t)blockIdx.x * DM_BN;
+  const int KT = (int)((p.T + DM_BK - 1) / DM_BK);
+
+  if (tid == 0) {
+    for (int s = 0; s < WS_STAGES; s++) { mbar_init(&full[s], 32 * NPW); mbar_init(&empty[s], NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= NCW) {
+    // ===== producers: NPW warps share the rows of both tiles of every stage =====
+    const int pw = warp - NCW;
+    // loop-invariant parts of the aligned copy pattern
+    const int a_kc = (lane & 7) * 2;
+    const int a_dst = (lane >> 3) * DM_LDA + a_kc;
+    const double *a_src = A + (h0 + (lane >> 3)) * p.iah + a_kc;
+    unsigned a_mask = 0;
+    for (int i = 0; i < 32; i++) if (h0 + (lane >> 3) + 4 * i < p.H) a_mask |= 1u << i;
+    const int b_dst = lane * 2;
+    const double *b_src = B + w0 + lane * 2;
+    int b_bytes[2];
+    for (int q = 0; q < 2; q++) {
+      const int64_t w = w0 + lane * 2 + 64 * q;
+      b_bytes[q] = (w < p.W) ? ((p.W - w >= 2) ? 16 : 8) : 0;
+    }
+    for (int kt = 0; kt < KT; kt++) {
+      const int s = kt % WS_STAGES;
+      if (kt >= WS_STAGES) mbar_wait(&empty[s], ((kt / WS_STAGES) - 1) & 1);
+      const int64_t k0 = (int64_t)kt * DM_BK;
+      double *dA = sA + s * DM_A_STAGE;
+      double *dB = sB + s * DM_B_STAGE;
+      if (ALIGNED16) {
+        // lean issue loop: row validity (A) and column validity (B) are loop-invariant and were
+        // folded into a_mask / b_bytes before the k loop; per copy = 1 address add + 1 LDGSTS
+        const int64_t k = k0 + a_kc;
+        const int kvalid = (k < p.T) ? ((p.T - k >= 2) ? 16 : 8) : 0;
+        const double *ga = a_src + k0;
+        double *da = dA + a_dst;
+#pragma unroll
+        for (int j = 0; j < 32 / NPW; j++) {      // A: rows (lane>>3) + 4i, i = pw + NPW*j
+          const int i = pw + NPW * j;
+          const int valid = ((a_mask >> i) & 1u) ? kvalid : 0;
+          cp_async(da + (4 * i) * DM_LDA, valid ? (ga + (int64_t)(4 * i) * p.iah) : A, valid, true);
+        }
+        const int64_t krem = p.T - k0;             // k-rows of this tile that exist
+        const double *gb = b_src + k0 * p.ibt;
+        double *db = dB + b_dst;
+#pragma unroll
+        for (int j = 0; j < 32 / NPW; j++) {      // B: k-row i>>1, chunk lane + 32*(i&1)
+          const int i = pw + NPW * j;
+          const int r = i >> 1;
+          const int valid = (r < krem) ? b_bytes[i & 1] : 0;
+          cp_async(db + r * DM_LDB + 64 * (i & 1), valid ? (gb + (int64_t)r * p.ibt + 64 * (i & 1)) : B, valid, true);
+        }
+      } else {
+        const int kc = lane & 15;
+        const int64_t k = k0 + kc;
+#pragma unroll 8
+        for (int i = pw; i < 64; i += NPW) {      // A: rows (lane>>4) + 2i, element lane&15
+          const int r = (lane >> 4) + 2 * i;
+          const int64_t h = h0 + r;
+          const int valid = (h < p.H && k < p.T) ? 8 : 0;
+          cp_async(dA + r * DM_LDA + kc, valid ? (A + h * p.iah + k) : A, valid, false);
+        }
+#pragma unroll 8
+        for (int i = pw; i < 64; i += NPW) {      // B: k-row i>>2, element lane + 32*(i&3)
+          const int r = i >> 2, wc = lane + 32 * (i & 3);
+          const int64_t kk = k0 + r, w = w0 + wc;
+          const int valid = (kk < p.T && w < p.W) ? 8 : 0;
+          cp_async(dB + r * DM_LDB + wc, valid ? (B + kk * p.ibt + w) : B, valid, false);
+        }
+      }
+      mbar_arrive_cp_async(&full[s]);
+    }
+    cp_wait<0>();
+    return;
+  }
+
+  // ===== consumers =====
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t4 = lane & 3;
+  double acc[MT][4][2];
+#pragma unroll
+  for (int i = 0; i < MT; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  for (int kt = 0; kt < KT; kt++) {
+    const int s = kt % WS_STAGES;
+    mbar_wait(&full[s], (kt / WS_STAGES) & 1);
+    const double *tA = sA + s * DM_A_STAGE + (wm * MT * 8) * DM_LDA;
+    const double *tB = sB + s * DM_B_STAGE + wn * 32;
+#pragma unroll
+    for (int ks = 0; ks < DM_BK; ks += 4) {
+      double af[MT], bf[4];
+#pragma unroll
+      for (int i = 0; i < MT; i++) af[i] = tA[(i * 8 + g) * DM_LDA + ks + t4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) bf[j] = tB[(ks + t4) * DM_LDB + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < MT; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  const bool c_vec = (p.icw == 1) && ((((uintptr_t)C) & 15) == 0) && ((p.ich & 1) == 0);
+#pragma unroll
+  for (int i = 0; i < MT; i++) {
+    const int64_t h = h0 + wm * MT * 8 + i * 8 + g;
+    if (h >= p.H) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int64_t w = w0 + wn * 32 + j * 8 + t4 * 2;
+      if (w >= p.W) continue;
+      double *dst = C + h * p.ich + w * p.icw;
+      if (c_vec && w + 1 < p.W) {
+        *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+      } else {
+        dst[0] = acc[i][j][0];
+        if (w + 1 < p.W) dst[p.icw] = acc[i][j][1];
+      }
+    }
+  }
+}
+
+template <bool ALIGNED16, int NCW, int STAGES, int NPW>
+static int dmma_ws_go(const MmPlan &p, dim3 grid, cudaStream_t s, const Err &E) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_ws_kernel<ALIGNED16, NCW, STAGES, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem(STAGES)), E);
+    attr_set = true;
+  }
+  mm_dmma_ws_kernel<ALIGNED16, NCW, STAGES, NPW><<<grid, NCW * 32 + NPW * 32, ws_smem(STAGES), s>>>(p);
+  return PDLB200_OK;
+}
+
 int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
   // eligibility: unit stride along t in a and along w in b (PDL's default physical layout)
   if (p.T == 0) return PDLB200_EUNSUPPORTED;
@@ -233,7 +430,17 @@ int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
   cudaStream_t s = (cudaStream_t)t->stream;
   const char *sh = getenv("PDLB200_DMMA_SHAPE");
   const int shape = (sh && !strcmp(sh, "884")) ? 0 : 1;
+  const char *var = getenv("PDLB200_DMMA");            // "sync" = the __syncthreads pipeline; default warp-specialised
   int rc;
+  if (!(var && !strcmp(var, "sync"))) {
+    const char *name = "matmult_dmma_ws16_p4";
+    if (!aligned) { rc = dmma_ws_go<false, 16, 4, 2>(p, grid, s, E); name = "matmult_dmma_ws16_v8"; }
+    else          { rc = dmma_ws_go<true, 16, 4, 4>(p, grid, s, E); }
+    if (rc) return rc;
+    note_launch(name);
+    PDLB200_CUDA_OK(cudaGetLastError(), E);
+    return PDLB200_OK;
+  }
   if (aligned) rc = shape ? dmma_go<true, 1>(p, grid, s, E) : dmma_go<true, 0>(p, grid, s, E);
   else         rc = shape ? dmma_go<false, 1>(p, grid, s, E) : dmma_go<false, 0>(p, grid, s, E);
   if (rc) return rc;
