@@ -22,12 +22,16 @@
 // Integer, min/max and index results are therefore bit-exact however a row is cut; float
 // sums differ from the reference only by summation order.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace pdlb200 {
 
 constexpr int RD_THREADS = 256;
-constexpr int RD_UNROLL = 4;
+// 128-bit loads a thread keeps in flight per trip (R::kUnroll).  HBM-bound streaming needs ~100+ KB in
+// flight per SM: reducers whose hot loop fits 32 registers run 8 CTAs/SM with 4 loads each; heavier
+// ones (64-bit accumulators, min/max with index) get 6 CTAs/SM and compensate with 8 loads.
+constexpr int RD_UNROLL_MAX = 8;
 
 struct RdPlan {
   const char *a; char *b;       // bases with offs applied
@@ -75,6 +79,8 @@ constexpr int64_t RD_NOIDX = 0x7fffffffffffffffll;
 // sumover / dsumover: tmp += a over good elements; no good element in bad mode -> BAD (Ufunc.pd:102-110)
 template <class T, class O> struct RSum {
   static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = (sizeof(O) <= 4) ? 4 : 8;
   struct Loc { O s; int32_t any; };
   struct Acc { O s; int32_t any; int32_t pad; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.any = 0; return x; }
@@ -94,6 +100,8 @@ template <class T, class O> struct RSum {
 // second pass over [0, z) for rows that have one (kPrefix).
 template <class T, class O> struct RProd {
   static constexpr bool kPrefix = !tt<O>::is_int;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = (sizeof(O) <= 4 && tt<O>::is_int) ? 4 : 8;
   struct Loc { O s; int32_t any; int32_t z; };
   struct Acc { O s; int32_t any; int32_t pad; int64_t z; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(1); x.any = 0; x.z = 0x7fffffff; return x; }
@@ -116,6 +124,8 @@ template <class T, class O> struct RProd {
 // conversions (cnt is PDL_Indx = int64); cnt == 0 -> BAD (bad mode) or 0 / NaN (good mode).
 template <class T, class O> struct RAvg {
   static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = (sizeof(O) <= 4) ? 4 : 8;
   struct Loc { O s; int32_t cnt; };
   struct Acc { O s; int64_t cnt; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.cnt = 0; return x; }
@@ -140,8 +150,10 @@ template <class T, class O> struct RAvg {
 // yet" encoded as idx < 0 (and cur = NaN for float types so one test covers both).  Closed form used
 // by the merge: the first-in-index-order extreme of the non-NaN good values; if every good value is
 // NaN, the LAST NaN; if there is no good value, BAD.
-template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
+template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMaxExact {
   static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = 8;
   struct Loc { T cur; int32_t idx; };
   struct Acc { T cur; int64_t idx; int32_t state; int32_t pad; };  // state 0 empty, 1 non-NaN, 2 NaN only
   static __device__ __forceinline__ Loc linit() {
@@ -179,10 +191,46 @@ template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
     else *out = (O)x.cur;
   }
 };
+// Hot-loop version of the same reducer: cur starts at the identity (+inf / type max for minimum,
+// -inf / type min for maximum) and an element is taken iff it is STRICTLY better — two instructions
+// fewer per element than the exact rule (no "cur is NaN / nothing taken yet" test), NaNs are never
+// taken.  What it cannot represent is a thread whose good elements are all equal to the identity or
+// NaN: then nothing was taken (idx < 0) and the kernel re-walks just that thread's elements with
+// RMinMaxExact (kRescan).  Acc / merge / finish are the exact reducer's, so results are identical.
+template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
+  using Exact = RMinMaxExact<T, O, ISMAX, WANT_IND>;
+  using Acc = typename Exact::Acc;
+  static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = true;
+  static constexpr int kUnroll = 8;
+  struct Loc { T cur; int32_t idx; };
+  static __device__ __forceinline__ T identity() {
+    if constexpr (sizeof(T) == 4 && !tt<T>::is_int) return __uint_as_float(ISMAX ? 0xff800000u : 0x7f800000u);
+    else if constexpr (!tt<T>::is_int) return __longlong_as_double(ISMAX ? (long long)0xfff0000000000000ull : 0x7ff0000000000000ll);
+    else if constexpr (tt<T>::is_uns) return ISMAX ? T(0) : T(~T(0));
+    else { using U = typename std::make_unsigned<T>::type; const T mx = (T)(U(~U(0)) >> 1); return ISMAX ? (T)(-mx - 1) : mx; }
+  }
+  static __device__ __forceinline__ Loc linit() { Loc x; x.cur = identity(); x.idx = -1; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t rel) {
+    const bool take = ISMAX ? (v > x.cur) : (v < x.cur);
+    x.cur = take ? v : x.cur;
+    x.idx = take ? rel : x.idx;
+  }
+  static __device__ __forceinline__ bool needs_rescan(const Loc &l) { return l.idx < 0; }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t lo) {
+    Acc x; x.cur = l.cur; x.idx = lo + l.idx; x.state = 1; x.pad = 0; return x;
+  }
+  static __device__ __forceinline__ Acc init() { return Exact::init(); }
+  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { return Exact::merge(l, r); }
+  static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) { Exact::finish(x, p, out); }
+};
+
 // andover orover zcover xorover (logical) and bandover borover bxorover (bitwise), Ufunc.pd:143-187.
 // KIND: 0 and, 1 or, 2 zc, 3 xor, 4 band, 5 bor, 6 bxor.  Output type == input type.
 template <class T, int KIND> struct RBits {
   static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = (sizeof(T) <= 4) ? 4 : 8;
   using U = typename tt<T>::wide_u;
   struct Acc { U v; int32_t any; };
   using Loc = Acc;
@@ -220,6 +268,8 @@ template <class T, int KIND> struct RBits {
 // lpush, so the accumulator counts those; nbad = n - ngood (good mode: nbad = 0, ngood = n).
 template <class T, bool GOOD> struct RCount {
   static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = 4;
   struct Loc { int32_t cnt; };
   struct Acc { int64_t cnt; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.cnt = 0; return x; }
@@ -251,7 +301,7 @@ __device__ __forceinline__ void rd_row_k(typename R::Loc &loc, const T *row, int
   const T *base = row + lo * inc;         // element `rel` lives at base[rel * inc]
   const int32_t len = (int32_t)(hi - lo);
   if (inc == 1) {
-    // peel to 16-byte alignment, then 128-bit loads with RD_UNROLL in flight, then the tail
+    // peel to 16-byte alignment, then 128-bit loads with R::kUnroll in flight, then the tail
     const uintptr_t addr = (uintptr_t)base;
     int32_t head = (int32_t)(((16 - (addr & 15)) & 15) / sizeof(T));
     if (head > len) head = len;
@@ -259,12 +309,12 @@ __device__ __forceinline__ void rd_row_k(typename R::Loc &loc, const T *row, int
     const int32_t nv = (len - head) / VEC;
     const uint4 *vp = reinterpret_cast<const uint4 *>(base + head);
     int32_t j = lane;
-    for (; j + (RD_UNROLL - 1) * width < nv; j += RD_UNROLL * width) {
-      Pack<T> r[RD_UNROLL];
+    for (; j + (R::kUnroll - 1) * width < nv; j += R::kUnroll * width) {
+      Pack<T> r[R::kUnroll];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) r[u].q = vp[j + u * width];
+      for (int u = 0; u < R::kUnroll; u++) r[u].q = vp[j + u * width];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) {
+      for (int u = 0; u < R::kUnroll; u++) {
         const int32_t e0 = head + (j + u * width) * VEC;
 #pragma unroll
         for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r[u].e[k], e0 + k, abad);
@@ -279,12 +329,12 @@ __device__ __forceinline__ void rd_row_k(typename R::Loc &loc, const T *row, int
     for (int32_t i = head + nv * VEC + lane; i < len; i += width) rd_push<R, T, BADK>(loc, base[i], i, abad);
   } else {
     int32_t i = lane;
-    for (; i + (RD_UNROLL - 1) * width < len; i += RD_UNROLL * width) {
-      T v[RD_UNROLL];
+    for (; i + (R::kUnroll - 1) * width < len; i += R::kUnroll * width) {
+      T v[R::kUnroll];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) v[u] = base[(int64_t)(i + u * width) * inc];
+      for (int u = 0; u < R::kUnroll; u++) v[u] = base[(int64_t)(i + u * width) * inc];
 #pragma unroll
-      for (int u = 0; u < RD_UNROLL; u++) rd_push<R, T, BADK>(loc, v[u], i + u * width, abad);
+      for (int u = 0; u < R::kUnroll; u++) rd_push<R, T, BADK>(loc, v[u], i + u * width, abad);
     }
     for (; i < len; i += width) rd_push<R, T, BADK>(loc, base[(int64_t)i * inc], i, abad);
   }
@@ -376,7 +426,15 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
     const T *rp = reinterpret_cast<const T *>(p.a) + oa;
     typename R::Loc loc = R::linit();
     rd_row<R, T, BAD>(loc, rp, lo, hi, p.inc_n, lane, width, abad, abadnan);
-    Acc acc = rd_group_reduce<R, MODE>(R::lift(loc, lo), smem);
+    Acc mine;
+    if constexpr (R::kRescan) {
+      if (R::needs_rescan(loc)) {   // rare: this thread saw only identity-valued / NaN / BAD elements
+        typename R::Exact::Loc ex = R::Exact::linit();
+        rd_row<typename R::Exact, T, BAD>(ex, rp, lo, hi, p.inc_n, lane, width, abad, abadnan);
+        mine = R::Exact::lift(ex, lo);
+      } else mine = R::lift(loc, lo);
+    } else mine = R::lift(loc, lo);
+    Acc acc = rd_group_reduce<R, MODE>(mine, smem);
     const bool writer = (MODE == 0) || (MODE == 1 && lane == 0) || (MODE == 2 && threadIdx.x == 0);
     if (p.nchunks == 1) {
       O *out = reinterpret_cast<O *>(p.b) + ob;
