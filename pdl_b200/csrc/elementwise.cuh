@@ -150,60 +150,39 @@ ew_kernel(const __grid_constant__ EwPlan p) {
 // checks (FULL), only the last tile of a row pays for them.
 // Used when dim 0 is long enough to fill tiles (always for fully collapsed contiguous ndarrays).
 template <class T, int VEC>
-__device__ __forceinline__ void ew_load_full(Pack<T> &r, const T *p, int64_t st0, int vec_ok, const Pack<T> &bc, bool is_bc) {
+__device__ __forceinline__ void ew_load_full(Pack<T> &r, const T *p, int64_t st0, int vec_ok, T bc, bool is_bc) {
   using W = typename vec_word<VEC * sizeof(T)>::type;
-  if (is_bc) { r = bc; return; }
+  if (is_bc) {
+#pragma unroll
+    for (int k = 0; k < VEC; k++) r.e[k] = bc;
+    return;
+  }
   if (vec_ok) { *reinterpret_cast<W *>(&r) = *reinterpret_cast<const W *>(p); return; }
 #pragma unroll
   for (int k = 0; k < VEC; k++) r.e[k] = p[k * st0];
 }
 
-template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL, bool FULL>
-__device__ __forceinline__ void ew_tile_body(const EwPlan &p, const TI *pa, const TI *pb, TO *pc, int64_t left0,
-                                             int64_t sa0, int64_t sb0, int64_t sc0, int64_t ja, int64_t jb, int64_t jc,
-                                             const Pack<TI> &bca, const Pack<TI> &bcb, bool a_bc, bool b_bc,
-                                             TI abad, TI bbad, TO cbad) {
-  constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
-  Pack<TI> ra[UNROLL], rb[UNROLL];
+template <class Op, class TI, class TO, bool BAD, int NIN, int VEC>
+__device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI> &ra, const Pack<TI> &rb, TO *dst, int64_t sc0,
+                                                 int cnt, TI abad, TI bbad, TO cbad) {
+  Pack<TO> rc;
 #pragma unroll
-  for (int j = 0; j < UNROLL; j++) {
-    if (FULL) {
-      ew_load_full<TI, VEC>(ra[j], pa + j * ja, sa0, p.vec[0], bca, a_bc);
-      if (NIN > 1) ew_load_full<TI, VEC>(rb[j], pb + j * jb, sb0, p.vec[1], bcb, b_bc);
-    } else {
-      const int64_t left = left0 - (int64_t)j * EW_THREADS * VEC;
-      if (left > 0) {
-        const int cnt = left < VEC ? (int)left : VEC;
-        ew_load<TI, VEC>(ra[j], reinterpret_cast<const char *>(pa + j * ja), 0, sa0, p.vec[0], cnt);
-        if (NIN > 1) ew_load<TI, VEC>(rb[j], reinterpret_cast<const char *>(pb + j * jb), 0, sb0, p.vec[1], cnt);
-      }
+  for (int k = 0; k < VEC; k++) {
+    const TI a = ra.e[k];
+    const TI b = (NIN > 1) ? rb.e[k] : TI(0);
+    bool bad = false;
+    if constexpr (BAD) {
+      bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
+      if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
     }
+    const TO r = Op::template f<TI, TO>(a, b);
+    rc.e[k] = bad ? cbad : r;
   }
-#pragma unroll
-  for (int j = 0; j < UNROLL; j++) {
-    const int64_t left = FULL ? VEC : left0 - (int64_t)j * EW_THREADS * VEC;
-    if (FULL || left > 0) {
-      const int cnt = (FULL || left >= VEC) ? VEC : (int)left;
-      Pack<TO> rc;
-#pragma unroll
-      for (int k = 0; k < VEC; k++) {
-        const TI a = ra[j].e[k];
-        const TI b = (NIN > 1) ? rb[j].e[k] : TI(0);
-        bool bad = false;
-        if constexpr (BAD) {
-          bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
-          if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
-        }
-        const TO r = Op::template f<TI, TO>(a, b);
-        rc.e[k] = bad ? cbad : r;
-      }
-      ew_store<TO, VEC>(rc, reinterpret_cast<char *>(pc + j * jc), 0, sc0, p.vec[NIN], cnt);
-    }
-  }
+  ew_store<TO, VEC>(rc, reinterpret_cast<char *>(dst), 0, sc0, p.vec[NIN], cnt);
 }
 
 template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 4)
 ew_tile_kernel(const __grid_constant__ EwPlan p) {
   constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
   constexpr int64_t TILE = (int64_t)EW_THREADS * UNROLL * VEC;
@@ -236,20 +215,34 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
     const TI *pa = reinterpret_cast<const TI *>(p.ptr[0]) + oa + i_first * sa0;
     const TI *pb = reinterpret_cast<const TI *>(p.ptr[NIN > 1 ? 1 : 0]) + ob + i_first * sb0;
     TO *pc = reinterpret_cast<TO *>(p.ptr[NIN]) + oc + i_first * sc0;
-    Pack<TI> bca, bcb;                    // dummy-dim operands: one load per work item
-    if (a_bc) { const TI v = *pa;
-#pragma unroll
-      for (int k = 0; k < VEC; k++) bca.e[k] = v; }
-    if (b_bc) { const TI v = *pb;
-#pragma unroll
-      for (int k = 0; k < VEC; k++) bcb.e[k] = v; }
+    const TI bca = a_bc ? *pa : TI(0);    // dummy-dim operands: one load per work item
+    const TI bcb = b_bc ? *pb : TI(0);
 
     for (int64_t seg = seg0; seg < seg1; seg++, i_first += TILE, pa += UNROLL * ja, pb += UNROLL * jb, pc += UNROLL * jc) {
-      const int64_t tile_end = (seg + 1) * TILE;
-      if (tile_end <= p.dims[0])
-        ew_tile_body<Op, TI, TO, BAD, NIN, UNROLL, true>(p, pa, pb, pc, 0, sa0, sb0, sc0, ja, jb, jc, bca, bcb, a_bc, b_bc, abad, bbad, cbad);
-      else
-        ew_tile_body<Op, TI, TO, BAD, NIN, UNROLL, false>(p, pa, pb, pc, p.dims[0] - i_first, sa0, sb0, sc0, ja, jb, jc, bca, bcb, a_bc, b_bc, abad, bbad, cbad);
+      if ((seg + 1) * TILE <= p.dims[0]) {
+        // full tile: no bounds checks; all loads of the tile are issued before the first use
+        Pack<TI> ra[UNROLL], rb[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+          ew_load_full<TI, VEC>(ra[j], pa + j * ja, sa0, p.vec[0], bca, a_bc);
+          if (NIN > 1) ew_load_full<TI, VEC>(rb[j], pb + j * jb, sb0, p.vec[1], bcb, b_bc);
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++)
+          ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra[j], rb[NIN > 1 ? j : 0], pc + j * jc, sc0, VEC, abad, bbad, cbad);
+      } else {
+        // last (partial) tile of a row: one unit at a time
+#pragma unroll 1
+        for (int j = 0; j < UNROLL; j++) {
+          const int64_t left = p.dims[0] - i_first - (int64_t)j * EW_THREADS * VEC;
+          if (left <= 0) break;
+          const int cnt = left < VEC ? (int)left : VEC;
+          Pack<TI> ra, rb;
+          ew_load<TI, VEC>(ra, reinterpret_cast<const char *>(pa + j * ja), 0, sa0, p.vec[0], cnt);
+          if (NIN > 1) ew_load<TI, VEC>(rb, reinterpret_cast<const char *>(pb + j * jb), 0, sb0, p.vec[1], cnt);
+          ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra, rb, pc + j * jc, sc0, cnt, abad, bbad, cbad);
+        }
+      }
     }
   }
 }
