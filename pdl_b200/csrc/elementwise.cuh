@@ -27,6 +27,9 @@ struct EwPlan {
   int64_t vpr;                 // vectors per row = ceil(dims[0]/VEC)   (tile kernel: tiles per row)
   int64_t ipr;                 // tile kernel: work items per row
   int grp;                     // tile kernel: consecutive tiles of one row per work item
+  int rowrep;                  // tile kernel: consecutive dim-1 rows per work item (>1 only when an input is
+                               //   constant along dim 1: its tile is then loaded once and reused from registers)
+  int64_t nblk1;               // ceil(dims[1] / rowrep)
   uint64_t bad[3];             // badvalue bits per operand
   int nd;
   int badnan[3];
@@ -181,8 +184,10 @@ __device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI>
   ew_store<TO, VEC>(rc, reinterpret_cast<char *>(dst), 0, sc0, p.vec[NIN], cnt);
 }
 
+// 64 registers (4 CTAs/SM) for the good-mode bodies; the BAD bodies carry the extra compares/selects and
+// get 80 (3 CTAs/SM) rather than spilling inside the hot loop.
 template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
-__global__ void __launch_bounds__(EW_THREADS, 4)
+__global__ void __launch_bounds__(EW_THREADS, BAD ? 3 : 4)
 ew_tile_kernel(const __grid_constant__ EwPlan p) {
   constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
   constexpr int64_t TILE = (int64_t)EW_THREADS * UNROLL * VEC;
@@ -194,13 +199,25 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
   const int64_t ja = (int64_t)EW_THREADS * VEC * sa0, jb = (int64_t)EW_THREADS * VEC * sb0, jc = (int64_t)EW_THREADS * VEC * sc0;
   const bool a_bc = (sa0 == 0) && !p.vec[0], b_bc = (NIN > 1) && (sb0 == 0) && !p.vec[1];
 
+  const int64_t sa1 = (p.nd > 1) ? p.st[0][1] : 0, sb1 = (NIN > 1 && p.nd > 1) ? p.st[1][1] : 0, sc1 = (p.nd > 1) ? p.st[NIN][1] : 0;
+  const bool a_inv = p.rowrep > 1 && sa1 == 0, b_inv = (NIN > 1) && p.rowrep > 1 && sb1 == 0;
+
   for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
     int64_t row = 0, it = item;
     int64_t oa = 0, ob = 0, oc = 0;
+    int rows_here = 1;
     if (p.nd > 1) {
       row = item / ipr; it = item - row * ipr;
       int64_t r = row;
-      for (int d = 1; d < p.nd; d++) {
+      {   // dim 1 is walked in blocks of `rowrep` rows
+        const int64_t q = (p.nd == 2) ? 0 : r / p.nblk1;
+        const int64_t i1 = (r - q * p.nblk1) * p.rowrep;
+        const int64_t rem = p.dims[1] - i1;
+        rows_here = rem < p.rowrep ? (int)rem : p.rowrep;
+        oa += i1 * sa1; if (NIN > 1) ob += i1 * sb1; oc += i1 * sc1;
+        r = q;
+      }
+      for (int d = 2; d < p.nd; d++) {
         const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d];
         const int64_t i = r - q * p.dims[d];
         oa += i * p.st[0][d];
@@ -215,32 +232,42 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
     const TI *pa = reinterpret_cast<const TI *>(p.ptr[0]) + oa + i_first * sa0;
     const TI *pb = reinterpret_cast<const TI *>(p.ptr[NIN > 1 ? 1 : 0]) + ob + i_first * sb0;
     TO *pc = reinterpret_cast<TO *>(p.ptr[NIN]) + oc + i_first * sc0;
-    const TI bca = a_bc ? *pa : TI(0);    // dummy-dim operands: one load per work item
-    const TI bcb = b_bc ? *pb : TI(0);
 
     for (int64_t seg = seg0; seg < seg1; seg++, i_first += TILE, pa += UNROLL * ja, pb += UNROLL * jb, pc += UNROLL * jc) {
       if ((seg + 1) * TILE <= p.dims[0]) {
-        // full tile: no bounds checks; all loads of the tile are issued before the first use
+        // full tile: no bounds checks; all loads of the tile are issued before the first use.  Inputs that
+        // are constant along dim 1 are loaded for the first row of the block only.
         Pack<TI> ra[UNROLL], rb[UNROLL];
+        for (int rr = 0; rr < rows_here; rr++) {
+          const TI *qa = pa + rr * sa1;
+          const TI *qb = pb + rr * sb1;
+          if (rr == 0 || !a_inv) {
+            const TI bca = a_bc ? *qa : TI(0);    // dummy along dim 0: one load per row
 #pragma unroll
-        for (int j = 0; j < UNROLL; j++) {
-          ew_load_full<TI, VEC>(ra[j], pa + j * ja, sa0, p.vec[0], bca, a_bc);
-          if (NIN > 1) ew_load_full<TI, VEC>(rb[j], pb + j * jb, sb0, p.vec[1], bcb, b_bc);
+            for (int j = 0; j < UNROLL; j++) ew_load_full<TI, VEC>(ra[j], qa + j * ja, sa0, p.vec[0], bca, a_bc);
+          }
+          if (NIN > 1 && (rr == 0 || !b_inv)) {
+            const TI bcb = b_bc ? *qb : TI(0);
+#pragma unroll
+            for (int j = 0; j < UNROLL; j++) ew_load_full<TI, VEC>(rb[j], qb + j * jb, sb0, p.vec[1], bcb, b_bc);
+          }
+#pragma unroll
+          for (int j = 0; j < UNROLL; j++)
+            ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra[j], rb[NIN > 1 ? j : 0], pc + rr * sc1 + j * jc, sc0, VEC, abad, bbad, cbad);
         }
-#pragma unroll
-        for (int j = 0; j < UNROLL; j++)
-          ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra[j], rb[NIN > 1 ? j : 0], pc + j * jc, sc0, VEC, abad, bbad, cbad);
       } else {
         // last (partial) tile of a row: one unit at a time
+        for (int rr = 0; rr < rows_here; rr++) {
 #pragma unroll 1
-        for (int j = 0; j < UNROLL; j++) {
-          const int64_t left = p.dims[0] - i_first - (int64_t)j * EW_THREADS * VEC;
-          if (left <= 0) break;
-          const int cnt = left < VEC ? (int)left : VEC;
-          Pack<TI> ra, rb;
-          ew_load<TI, VEC>(ra, reinterpret_cast<const char *>(pa + j * ja), 0, sa0, p.vec[0], cnt);
-          if (NIN > 1) ew_load<TI, VEC>(rb, reinterpret_cast<const char *>(pb + j * jb), 0, sb0, p.vec[1], cnt);
-          ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra, rb, pc + j * jc, sc0, cnt, abad, bbad, cbad);
+          for (int j = 0; j < UNROLL; j++) {
+            const int64_t left = p.dims[0] - i_first - (int64_t)j * EW_THREADS * VEC;
+            if (left <= 0) break;
+            const int cnt = left < VEC ? (int)left : VEC;
+            Pack<TI> ra, rb;
+            ew_load<TI, VEC>(ra, reinterpret_cast<const char *>(pa + rr * sa1 + j * ja), 0, sa0, p.vec[0], cnt);
+            if (NIN > 1) ew_load<TI, VEC>(rb, reinterpret_cast<const char *>(pb + rr * sb1 + j * jb), 0, sb0, p.vec[1], cnt);
+            ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra, rb, pc + rr * sc1 + j * jc, sc0, cnt, abad, bbad, cbad);
+          }
         }
       }
     }
@@ -272,9 +299,22 @@ int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *
     if (grp > 8) grp = 8;
     if (grp > tpr) grp = tpr;
     if (grp < 1) grp = 1;
+    // an input that is constant along dim 1 (dummy dim / row vector) is kept in registers across a block of rows
+    p.rowrep = 1; p.nblk1 = (p.nd > 1) ? p.dims[1] : 1;
+    int64_t rowblocks = rows;
+    if (p.nd > 1 && p.dims[1] > 1 && (p.st[0][1] == 0 || (NIN > 1 && p.st[1][1] == 0))) {
+      int64_t rep = p.dims[1] < 16 ? p.dims[1] : 16;
+      // keep enough work items to fill the GPU
+      while (rep > 1 && tpr * (rows / p.dims[1]) * ((p.dims[1] + rep - 1) / rep) < (int64_t)sm_count() * 8) rep /= 2;
+      if (rep > 1) {
+        p.rowrep = (int)rep; p.nblk1 = (p.dims[1] + rep - 1) / rep;
+        rowblocks = (rows / p.dims[1]) * p.nblk1;
+        grp = 1;
+      }
+    }
     p.grp = (int)grp;
     p.ipr = (tpr + grp - 1) / grp;
-    p.vpr = tpr; p.n_units = p.ipr * rows;
+    p.vpr = tpr; p.n_units = p.ipr * rowblocks;
     const int64_t cap = (int64_t)sm_count() * 32;
     const int grid = (int)(p.n_units < cap ? p.n_units : cap);
     if (t->bvalflag) ew_tile_kernel<Op, TI, TO, true, NIN, TU><<<grid, EW_THREADS, 0, s>>>(p);
