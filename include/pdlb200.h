@@ -170,7 +170,8 @@ PDLB200_API int    pdlb200_memcpy_d2h(void *dst, const void *src, size_t nbytes,
  * same pointer; pages migrate on demand in both directions (= lazy host sync, done by the
  * driver), and chained device ops never cross PCIe.  See perl/PDL-B200/B200.xs. */
 PDLB200_API void  *pdlb200_managed_alloc(size_t nbytes);
-PDLB200_API void   pdlb200_managed_free(void *p);
+PDLB200_API void   pdlb200_managed_free(void *p);   /* returns the block to an exact-size free list */
+PDLB200_API void   pdlb200_managed_trim(void);      /* hand every cached block back to the driver */
 /* 0 = plain host memory, 1 = device memory, 2 = managed, 3 = pinned host (device-visible) */
 PDLB200_API int    pdlb200_ptr_kind(const void *p);
 /* Migrate a managed range towards the device (to_device != 0) or the host ahead of use. */

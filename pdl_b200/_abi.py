@@ -67,7 +67,7 @@ SYMBOLS = [
     "pdlb200_buf_upload", "pdlb200_buf_download", "pdlb200_buf_device_dirty",
     "pdlb200_abi_version", "pdlb200_device_count", "pdlb200_set_device", "pdlb200_sm_count",
     "pdlb200_sync", "pdlb200_host_alloc", "pdlb200_host_free", "pdlb200_memcpy_h2d",
-    "pdlb200_memcpy_d2h", "pdlb200_managed_alloc", "pdlb200_managed_free", "pdlb200_ptr_kind",
+    "pdlb200_memcpy_d2h", "pdlb200_managed_alloc", "pdlb200_managed_free", "pdlb200_managed_trim", "pdlb200_ptr_kind",
     "pdlb200_prefetch", "pdlb200_launch_count", "pdlb200_last_kernel", "pdlb200_op_name",
     "pdlb200_type_size",
 ]

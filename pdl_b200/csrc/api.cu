@@ -4,7 +4,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 #include "common.cuh"
 
 namespace pdlb200 {
@@ -52,6 +54,19 @@ void *scratch(size_t nbytes, cudaStream_t s) {
     g_scratch_sz[dev] = want;
   }
   return g_scratch[dev];
+}
+
+static std::unordered_multimap<size_t, void *> g_managed_free;   // exact-size free list
+static std::unordered_map<void *, size_t> g_managed_size;         // live managed blocks
+static size_t g_managed_cached = 0;
+static size_t managed_cache_cap() {
+  static size_t cap = 0;
+  if (!cap) {
+    const char *e = getenv("PDLB200_MANAGED_CACHE_MB");
+    cap = (size_t)(e ? atoll(e) : 16384) << 20;
+    if (!cap) cap = 1;
+  }
+  return cap;
 }
 
 static const char *op_names[PDLB200_OP__END] = {};
@@ -244,13 +259,62 @@ int pdlb200_buf_download(pdlb200_buf *b, void *host, size_t nbytes, int force, v
   return PDLB200_OK;
 }
 
+// Managed buffers are recycled through an exact-size free list: PDL scripts create same-sized
+// temporaries over and over (`$x = $y + $c` makes a fresh 32 MiB output per op), and
+// cudaMallocManaged + first-touch population + cudaFree cost ~2 ms per op against a 25 us kernel.
+// A recycled buffer is already resident in HBM; a new one is prefetched there so the producing
+// kernel does not take GPU page faults.  Cap: PDLB200_MANAGED_CACHE_MB (default 16384).
 void *pdlb200_managed_alloc(size_t nbytes) {
   if (probe_devices() <= 0) return nullptr;
+  if (!nbytes) nbytes = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_managed_free.find(nbytes);
+    if (it != g_managed_free.end()) {
+      void *p = it->second;
+      g_managed_free.erase(it);
+      g_managed_cached -= nbytes;
+      g_managed_size[p] = nbytes;
+      return p;
+    }
+  }
   void *p = nullptr;
-  if (cudaMallocManaged(&p, nbytes ? nbytes : 1, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaMallocManaged(&p, nbytes, cudaMemAttachGlobal) != cudaSuccess) {
+    cudaGetLastError();
+    pdlb200_managed_trim();   // give cached blocks back to the driver and retry once
+    if (cudaMallocManaged(&p, nbytes, cudaMemAttachGlobal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  if (nbytes >= (1u << 16)) cudaMemPrefetchAsync(p, nbytes, dev, (cudaStream_t)0);
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_managed_size[p] = nbytes;
   return p;
 }
-void pdlb200_managed_free(void *p) { if (p) cudaFree(p); }
+void pdlb200_managed_free(void *p) {
+  if (!p) return;
+  size_t nbytes = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_managed_size.find(p);
+    if (it != g_managed_size.end()) { nbytes = it->second; g_managed_size.erase(it); }
+    if (nbytes && g_managed_cached + nbytes <= managed_cache_cap()) {
+      g_managed_free.emplace(nbytes, p);
+      g_managed_cached += nbytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+void pdlb200_managed_trim(void) {
+  std::unordered_multimap<size_t, void *> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    drop.swap(g_managed_free);
+    g_managed_cached = 0;
+  }
+  for (auto &kv : drop) cudaFree(kv.second);
+}
 int pdlb200_ptr_kind(const void *p) {
   if (!p || probe_devices() <= 0) return 0;
   cudaPointerAttributes a;

@@ -404,8 +404,11 @@ __device__ __forceinline__ O rd_prod_prefix(const T *row, int64_t z, int64_t inc
 }
 
 // MODE: 0 thread/row, 1 warp/row, 2 CTA/row.  blockIdx.y = chunk of n.
+template <class R> constexpr int rd_min_blocks() { return R::kUnroll == 4 ? 8 : 5; }
+
+// launch bounds: the light reducers (kUnroll 4) are held to 32 registers = 8 CTAs/SM; the rest to 48 (5 CTAs)
 template <class R, class T, class O, bool BAD, int MODE>
-__global__ void __launch_bounds__(RD_THREADS)
+__global__ void __launch_bounds__(RD_THREADS, rd_min_blocks<R>())
 reduce_rows_kernel(const __grid_constant__ RdPlan p) {
   using Acc = typename R::Acc;
   const T abad = from_bits<T>(p.abad);
