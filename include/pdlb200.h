@@ -74,6 +74,8 @@ enum {
   PDLB200_OP_MATMULT = 60,
   /* type conversion, lib/PDL/Core/pdlconv.c:45-126,163-201 (converttypei) : a(); [o]b() of another type */
   PDLB200_OP_CONVERT = 61,
+  /* ipow, lib/PDL/Ops.pd:443-476 : a(); longlong b(); [o]ans() — exponentiation by squaring */
+  PDLB200_OP_IPOW = 62,
   PDLB200_OP__END
 };
 

@@ -57,7 +57,7 @@ OPS = {
     "andover": 40, "orover": 41, "bandover": 42, "borover": 43,
     "zcover": 44, "xorover": 45, "bxorover": 46, "nbadover": 47, "ngoodover": 48,
     "cumusumover": 50, "cumuprodover": 51, "dcumusumover": 52, "dcumuprodover": 53,
-    "matmult": 60, "converttype": 61,
+    "matmult": 60, "converttype": 61, "ipow": 62,
 }
 
 # every symbol include/pdlb200.h declares (tests check the .so exports them all)

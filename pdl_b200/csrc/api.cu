@@ -92,7 +92,7 @@ static void init_names() {
   N(PDLB200_OP_NBADOVER, "nbadover") N(PDLB200_OP_NGOODOVER, "ngoodover")
   N(PDLB200_OP_CUMUSUMOVER, "cumusumover") N(PDLB200_OP_CUMUPRODOVER, "cumuprodover")
   N(PDLB200_OP_DCUMUSUMOVER, "dcumusumover") N(PDLB200_OP_DCUMUPRODOVER, "dcumuprodover")
-  N(PDLB200_OP_MATMULT, "matmult") N(PDLB200_OP_CONVERT, "converttype")
+  N(PDLB200_OP_MATMULT, "matmult") N(PDLB200_OP_CONVERT, "converttype") N(PDLB200_OP_IPOW, "ipow")
 #undef N
 }
 
@@ -129,6 +129,7 @@ int launch_elementwise(const pdlb200_trans *t, const Err &E) {
   if (op <= PDLB200_OP_SPACESHIP) return ew_func(t, E);
   if (op <= PDLB200_OP_ABS2) return ew_unary(t, E);
   if (op == PDLB200_OP_CONVERT) return launch_convert(t, E);
+  if (op == PDLB200_OP_IPOW) return launch_ipow(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not an elementwise op", pdlb200_op_name(op));
 }
 
@@ -190,7 +191,7 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   Err E{err, errlen};
   if (int rc = validate(t, E)) return rc;
   const int op = t->op;
-  if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT) return launch_elementwise(t, E);
+  if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT || op == PDLB200_OP_IPOW) return launch_elementwise(t, E);
   if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);

@@ -105,6 +105,7 @@ void collapse_dims(const pdlb200_trans *t, Collapsed *c);
 // family launchers (one translation unit each)
 int launch_elementwise(const pdlb200_trans *t, const Err &E);
 int launch_convert(const pdlb200_trans *t, const Err &E);
+int launch_ipow(const pdlb200_trans *t, const Err &E);
 int launch_reduce(const pdlb200_trans *t, const Err &E);
 int launch_scan(const pdlb200_trans *t, const Err &E);
 int launch_matmult(const pdlb200_trans *t, const Err &E);

@@ -1,7 +1,11 @@
-// scan.cu — cumusumover / cumuprodover (+d variants), lib/PDL/Ufunc.pd:120-141:
-// a(n); [o]b(n).  First device version: one thread per row walks n sequentially, i.e. the
-// reference's own order, so float results are bit-exact too.  Coalesced when a broadcast dim is
-// the unit-stride one; a long single row is slow (decoupled look-back scan is future work).
+// scan.cu — cumusumover / cumuprodover (+d variants), lib/PDL/Ufunc.pd:120-141: a(n); [o]b(n).
+// Two kernels:
+//  * scan_rows_kernel: one thread per row walks n sequentially — the reference's own order, so float
+//    results are bit-exact; coalesced when a broadcast dim is the unit-stride one (many short rows).
+//  * scan_warp_kernel: one warp per row for long rows: 32 consecutive elements per step (coalesced),
+//    Kogge-Stone scan by shuffles, carry to the next step.  Integer results are bit-exact (wrap-around
+//    add/multiply is associative); float results differ from the sequential order only in rounding.
+// A single very long row still runs on one warp (a multi-CTA look-back scan is future work).
 #include <cstring>
 #include "common.cuh"
 namespace pdlb200 {
@@ -42,12 +46,85 @@ __global__ void __launch_bounds__(256) scan_rows_kernel(const __grid_constant__ 
   }
 }
 
+template <class O, bool PROD> __device__ __forceinline__ O scan_op(O a, O b) {
+  if constexpr (tt<O>::is_int) {
+    using U = typename tt<O>::wide_u;
+    return PROD ? (O)((U)a * (U)b) : (O)((U)a + (U)b);
+  } else return PROD ? a * b : a + b;
+}
+template <class O> __device__ __forceinline__ O shfl_up_t(O v, int d) {
+  if constexpr (sizeof(O) == 8) {
+    unsigned long long u; memcpy(&u, &v, 8);
+    u = __shfl_up_sync(0xffffffffu, u, d);
+    memcpy(&v, &u, 8); return v;
+  } else {
+    unsigned u; memcpy(&u, &v, 4);
+    u = __shfl_up_sync(0xffffffffu, u, d);
+    memcpy(&v, &u, 4); return v;
+  }
+}
+template <class O> __device__ __forceinline__ O shfl_idx_t(O v, int src) {
+  if constexpr (sizeof(O) == 8) {
+    unsigned long long u; memcpy(&u, &v, 8);
+    u = __shfl_sync(0xffffffffu, u, src);
+    memcpy(&v, &u, 8); return v;
+  } else {
+    unsigned u; memcpy(&u, &v, 4);
+    u = __shfl_sync(0xffffffffu, u, src);
+    memcpy(&v, &u, 4); return v;
+  }
+}
+
+template <class T, class O, bool PROD>
+__global__ void __launch_bounds__(256) scan_warp_kernel(const __grid_constant__ ScPlan p) {
+  const T abad = from_bits<T>(p.abad);
+  const O bbad = from_bits<O>(p.bbad);
+  const O ident = PROD ? O(1) : O(0);
+  const int lane = threadIdx.x & 31;
+  int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t row_step = (int64_t)gridDim.x * 8;
+  for (; row < p.nrows; row += row_step) {
+    int64_t oa = 0, ob = 0, r = row;
+    for (int d = 0; d < p.nd; d++) {
+      const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d];
+      const int64_t i = r - q * p.dims[d];
+      oa += i * p.sa[d]; ob += i * p.sb[d]; r = q;
+    }
+    const T *pa = reinterpret_cast<const T *>(p.a) + oa;
+    O *pb = reinterpret_cast<O *>(p.b) + ob;
+    O carry = ident;
+    for (int64_t n0 = 0; n0 < p.n; n0 += 32) {
+      const int64_t n = n0 + lane;
+      const bool in = n < p.n;
+      const T v = in ? pa[n * p.inc_a] : T(0);
+      const bool bad = in && p.badmode && is_bad(v, abad, p.abadnan != 0);
+      O x = (in && !bad) ? (O)v : ident;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const O y = shfl_up_t(x, d);
+        if (lane >= d) x = scan_op<O, PROD>(y, x);
+      }
+      const O res = scan_op<O, PROD>(carry, x);
+      if (in) pb[n * p.inc_b] = bad ? bbad : res;
+      carry = shfl_idx_t(res, 31);
+    }
+  }
+}
+
 template <class T, class O, bool PROD>
 static int scan_go(const ScPlan &p, cudaStream_t s, const char *name, const Err &E) {
-  int64_t g = (p.nrows + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
-  if (g > cap) g = cap;
-  scan_rows_kernel<T, O, PROD><<<(int)g, 256, 0, s>>>(p);
+  // long rows that are not laid out column-wise: one warp per row
+  const bool column = (p.nd >= 1) && (p.sa[0] == 1 || p.sa[0] == -1) && p.inc_a != 1 && p.dims[0] >= 32;
+  if (p.n >= 128 && !column) {
+    int64_t g = (p.nrows + 7) / 8;
+    if (g > cap) g = cap;
+    scan_warp_kernel<T, O, PROD><<<(int)g, 256, 0, s>>>(p);
+  } else {
+    int64_t g = (p.nrows + 255) / 256;
+    if (g > cap) g = cap;
+    scan_rows_kernel<T, O, PROD><<<(int)g, 256, 0, s>>>(p);
+  }
   note_launch(name);
   PDLB200_CUDA_OK(cudaGetLastError(), E);
   return PDLB200_OK;

@@ -41,4 +41,13 @@ def assgn(a, b):
     return run_op("assgn", [as_pdl(a, getattr(b, "engine", None))], [b])[0]
 
 
-__all__ = _BINARY + _UNARY + ["xor2", "not_", "abs_", "_rabs", "assgn"]
+def ipow(a, b, ans=None):
+    """PDL::ipow(a, b, [ans]): a ** b for integer b by squaring (lib/PDL/Ops.pd:443-476)."""
+    a = as_pdl(a)
+    if ans is None and a.is_inplace():
+        a._inplace = False
+        ans = a
+    return run_op("ipow", [a, as_pdl(b, a.engine)], [ans])[0]
+
+
+__all__ = ["ipow"] + _BINARY + _UNARY + ["xor2", "not_", "abs_", "_rabs", "assgn"]

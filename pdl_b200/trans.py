@@ -93,6 +93,9 @@ SPECS = {s.name: s for s in [
     OpSpec("cumuprodover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.L, tplus=True)], _A, "scan"),
     OpSpec("dcumusumover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.D)], _R, "scan"),
     OpSpec("dcumuprodover", [Par("a", ("n",)), Par("b", ("n",), out=True, typed=T.D)], _R, "scan"),
+    # ipow, lib/PDL/Ops.pd:443-476: GenericTypes [P Q, non-integer types with D last]
+    OpSpec("ipow", [Par("a"), Par("b", typed=T.LL), Par("ans", out=True)],
+           (T.ULL, T.LL, T.F, T.LD, T.CF, T.CD, T.CLD, T.D), "ufunc", inplace=("a", "ans")),
     # matmult, lib/PDL/Primitive.pd:191-195
     OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
 ]}

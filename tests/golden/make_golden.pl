@@ -110,6 +110,8 @@ sub add_case {
       $out = $args[0]->$m;
     } elsif ($kind eq 'matmult') {
       $out = $args[0] x $args[1];
+    } elsif ($kind eq 'ipow') {
+      $out = PDL::ipow($args[0], $args[1]);
     } elsif ($kind eq 'convert') {
       $out = $args[0]->convert($TOBJ{$call->{to}});
     } else { die "kind $kind" }
@@ -186,6 +188,13 @@ for my $t (qw(float double)) {
   add_case("abs-$t-special", [[mk($t,[22],'special')]], {kind=>'ufunc', op=>'abs'});
 }
 add_case("exp-long-to-double", [[mk('long',[6],'small')]], {kind=>'ufunc', op=>'exp'}, 4);
+# ipow (Ops.pd:443-476): a(); longlong b(); [o]ans()
+for my $t (qw(ulonglong longlong float double long)) {
+  my $base = mk($t,[12],'small'); $base->where($base == 0) .= 2 if $t =~ /long$/ ;   # 1/0 for negative powers kills the reference
+  my $e = pdl(longlong, [0,1,2,3,5,7,8,-1,-2,13,-3,4]);
+  add_case("ipow-$t", [[$base],[$e]], {kind=>'ipow'}, undef);
+  add_case("ipow-$t-scalar", [[mk($t,[7],'pos')], {scalar=>5, is_int=>1}], {kind=>'ipow'}, undef);
+}
 flush_cases('ufunc.json');
 
 # ---------------------------------------------------------------- type coercion + conversion (pdlapi.c:1182-1311, pdlconv.c:45-126)

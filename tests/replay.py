@@ -52,6 +52,8 @@ def run_call(call, args):
         return getattr(ufunc, call["op"])(args[0])
     if kind == "matmult":
         return P.matmult(args[0], args[1])
+    if kind == "ipow":
+        return ops.ipow(args[0], args[1])
     if kind == "convert":
         return args[0].convert(TYPE_ID[call["to"]])
     raise ValueError(kind)

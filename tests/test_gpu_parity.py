@@ -247,3 +247,40 @@ def test_matmult_default_path_double(engines):
     g, wnt = P.matmult(ga, gb).to_numpy(), P.matmult(oa, ob).to_numpy()
     bound = 2 * tt * np.finfo(np.float64).eps * (np.abs(a) @ np.abs(b))
     assert np.all(np.abs(g - wnt) <= bound)
+
+
+@pytest.mark.parametrize("t", [T.B, T.S, T.L, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_scans(engines, t):
+    rng = np.random.default_rng(1500 + t)
+    for (n, rows) in [(5, 3000), (1000, 37), (40_001, 2)]:          # thread-per-row and warp-per-row kernels
+        a = rand_array(rng, t, (rows, n), "exact" if t in (T.F, T.D) else "mixed")
+        for bad in (False, True):
+            src = a.copy()
+            if bad:
+                src[rng.random(src.shape) < 0.02] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+            for op in ("cumusumover", "dcumusumover", "cumuprodover"):
+                s2 = src
+                if op == "cumuprodover":
+                    if t in T.INTEGER:
+                        s2 = src
+                    else:
+                        s2 = np.where(src == np.array(T.DEFAULT_BAD[t]).astype(src.dtype), src,
+                                      np.where(rng.random(src.shape) < 0.5, 1.0, -1.0).astype(src.dtype))
+                (ga, oa) = both(engines, s2, t, bad)
+                assert_same(f"{op}-{T.NAMES[t]}-{n}x{rows}-bad{int(bad)}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa))
+    m = rand_array(rng, t, (64, 300), "exact" if t in (T.F, T.D) else "mixed")
+    outs = [ufunc.cumusumover(P.PDL.from_numpy(m, t, e).xchg(0, 1)) for e in engines]      # column layout
+    assert_same(f"cumusumover-xchg-{T.NAMES[t]}", outs[0], outs[1])
+
+
+@pytest.mark.parametrize("t", [T.ULL, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_ipow(engines, t):
+    from pdl_b200 import ops
+    rng = np.random.default_rng(1600 + t)
+    a = rand_array(rng, t, (20_001,), "pos" if t in T.INTEGER else "small")
+    if t in (T.F, T.D):
+        a[a == 0] = 1.5
+    e = rng.integers(-6 if t in (T.F, T.D) else 0, 13, size=a.shape).astype(np.int64)
+    (ga, oa), (ge, oe) = both(engines, a, t), both(engines, e, T.LL)
+    assert_same(f"ipow-{T.NAMES[t]}", ops.ipow(ga, ge), ops.ipow(oa, oe))       # same multiplication chain: bit-exact
+    assert_same(f"ipow-{T.NAMES[t]}-scalar", ops.ipow(ga, 3), ops.ipow(oa, 3))

@@ -1,0 +1,101 @@
+"""CPU: the Python mirror of the reference's host logic, checked against facts recorded from the
+real reference (SURVEY.md Appendix B and the cited source lines) with the oracle engine as backend."""
+import numpy as np
+import pytest
+
+import pdl_b200 as P
+from pdl_b200 import types as T, ufunc, ops
+from pdl_b200.trans import transtype_select, SPECS, par_type
+
+
+def test_scalar_typing_matches_pdlperl_h():
+    # lib/PDL/Core/pdlperl.h:185-205: IV -> smallest SIGNED type, NV -> double
+    assert T.scalar_type(1) == T.SB and T.scalar_type(300) == T.S and T.scalar_type(100000) == T.L
+    assert T.scalar_type(2**40) == T.IND and T.scalar_type(-2**40) == T.IND
+    assert T.scalar_type(2**63 + 5) == T.ULL
+    assert T.scalar_type(1.5) == T.D and T.scalar_type(float("nan")) == T.D
+
+
+def test_type_selection_rules(oracle_engine):
+    e = oracle_engine
+    f = P.PDL.from_numpy(np.array([1, 2], dtype=np.float32), T.F, e)
+    b = P.PDL.from_numpy(np.array([1, 2], dtype=np.uint8), T.B, e)
+    lng = P.PDL.from_numpy(np.array([2, 3], dtype=np.int32), T.L, e)
+    assert (f + 1.5).type == "double" and (f + 1).type == "float"          # Appendix B
+    assert (b + 1).type == "byte" and (b + 300).type == "short"
+    assert (lng ** 2).type == "double"                                      # power: GenericTypes [C.., F, LD, D]
+    assert (f << 1).type == "longlong"                                      # bit ops: last integer type
+    assert ufunc.sumover(b).type == "long" and ufunc.average(b).type == "long" and ufunc.minimum(b).type == "byte"
+    assert ufunc.dsumover(b).type == "double" and ufunc.maximum_ind(f).type == "indx"
+    # an existing output decides the type first (pdlapi.c:1216-1231)
+    out = P.PDL.empty(T.D, [2], e)
+    assert transtype_select(SPECS["plus"], [f, f, out]) == T.D
+    assert par_type(SPECS["sumover"].pars[1], T.B) == T.L and par_type(SPECS["sumover"].pars[1], T.D) == T.D
+
+
+def test_views_are_metadata_only(oracle_engine):
+    e = oracle_engine
+    a = P.sequence(T.D, 10, 10, engine=e)
+    s = a.slice("1:8:2,(3)")
+    assert s.dims == [4] and s.dimincs == [2] and s.offs == 31 and s.store is a.store
+    assert a.xchg(0, 1).dimincs == [10, 1]
+    assert P.sequence(T.D, 5, engine=e).dummy(0, 3).dimincs == [0, 1]       # Appendix B: dimincs 0,1
+    assert a.slice("-1:0:-3,:").to_numpy()[0].tolist() == [9, 6, 3, 0]
+    assert a.slice(":,*2,(0)").dims == [10, 2]
+    assert a.clump(-1).dims == [100] and a.flat().store is a.store           # physical parent: view
+    assert a.xchg(0, 1).flat().store is not a.store                          # strided parent: copied on device
+    with pytest.raises(P.PDLError):
+        a.slice("11,:")
+
+
+def test_broadcast_errors_and_empty(oracle_engine):
+    e = oracle_engine
+    with pytest.raises(P.PDLError, match="Mismatched implicit broadcast dimension 0: size 3 vs. 4"):
+        P.sequence(T.D, 3, engine=e) + P.sequence(T.D, 4, engine=e)
+    z = P.PDL.from_numpy(np.zeros((3, 0)), T.D, e)                           # dims [0,3]
+    assert (z + 1).dims == [0, 3]
+    assert ufunc.sumover(z).to_numpy().tolist() == [0, 0, 0]
+    m = ufunc.maximum(z)
+    assert m.badflag and np.all(m.to_numpy() == T.DEFAULT_BAD[T.D])          # Ufunc.pd:463-464, t/ufunc.t:99-104
+    with pytest.raises(P.PDLError, match=r"Dim mismatch in matmult of \[3x2\] x \[2x2\]: 3 != 2"):
+        P.matmult(P.sequence(T.D, 3, 2, engine=e), P.sequence(T.D, 2, 2, engine=e))
+
+
+def test_inplace_and_outputs(oracle_engine):
+    e = oracle_engine
+    a = P.sequence(T.L, 6, engine=e)
+    v = a.slice("1:-1:2")
+    v += 10                                                                   # writes through to the parent
+    assert a.to_numpy().tolist() == [0, 11, 2, 13, 4, 15]
+    r = a.inplace().plus(1) if hasattr(a, "plus") else ops.plus(a.inplace(), 1)
+    assert r is a and a.to_numpy().tolist() == [1, 12, 3, 14, 5, 16] and not a.is_inplace()
+    out = P.PDL.empty(T.L, [6], e)
+    assert ops.minus(a, 1, out, 1) is out and out.to_numpy().tolist() == [0, -11, -2, -13, -4, -15]  # swap: 1 - a
+    with pytest.raises(P.PDLError, match="can't broadcast over output"):
+        P.run_op("plus", [P.sequence(T.L, 6, 2, engine=e), a], [P.PDL.empty(T.L, [6], e)])
+
+
+def test_prepared_op_is_one_call(oracle_engine):
+    e = oracle_engine
+    a, b = P.sequence(T.F, 5, 4, engine=e), P.sequence(T.F, 5, engine=e)
+    out = P.PDL.empty(T.F, [5, 4], e)
+    prep = P.prepare_op("mult", [a, b], [out])
+    n0 = e.calls
+    prep(); prep()
+    assert e.calls == n0 + 2
+    assert np.array_equal(out.to_numpy(), a.to_numpy() * b.to_numpy())
+    with pytest.raises(P.PDLError, match="prepare_op needs inputs already"):
+        P.prepare_op("plus", [a, P.sequence(T.D, 5, engine=e)], [None])
+
+
+def test_badflag_propagation(oracle_engine):
+    e = oracle_engine
+    a = P.PDL.from_numpy(np.array([1, 2, 3], dtype=np.int32), T.L, e)
+    b = P.PDL.from_numpy(np.array([1, T.DEFAULT_BAD[T.L], 3], dtype=np.int32), T.L, e).set_badflag(True)
+    c = a + b
+    assert c.badflag and c.bad_mask().tolist() == [False, True, False]       # pdlapi.c:806-808, t/bad.t:27-46
+    assert not (a + a).badflag
+    # the OTHER operand holds the badvalue bit pattern but has no badflag: biop tests the state flag (Ops.pd:144)
+    d = P.PDL.from_numpy(np.array([T.DEFAULT_BAD[T.L], 5, 6], dtype=np.int32), T.L, e)
+    r = d + b
+    assert r.to_numpy()[0] == np.int32(T.DEFAULT_BAD[T.L]) + np.int32(1)      # computed (wraps), not forced BAD
