@@ -394,19 +394,19 @@ def main_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rows = 2048
-        sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step, 2 timed steps"
+        rows = 8192
+        sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step, 3 timed steps"
         try:
             if _have_ref():
-                r1 = run_reference_sample(rows, 2, 1, cores)
-                r0 = run_reference_sample(rows, 2, 1, 0)
+                r1 = run_reference_sample(rows, 3, 1, cores)
+                r0 = run_reference_sample(rows, 3, 1, 0)
                 cpu_baseline = {"value": r1["elements_per_sec"], "unit": "elements/s",
                                 "cores": int(r1.get("autopthread_actual") or 0) or 1, "kind": "reference",
                                 "sample": sample + f"; PDL {r1['pdl_version']} with autopthread ({r1.get('autopthread_actual')} threads)",
                                 "no_pthread": {"value": r0["elements_per_sec"], "cores": 1},
                                 "host_cores": cores}
             else:
-                r = run_port_sample(rows, 2, 1)
+                r = run_port_sample(rows, 3, 1)
                 cpu_baseline = {"value": r["elements_per_sec"], "unit": "elements/s", "cores": 1, "kind": "port",
                                 "sample": sample + "; oracle/pdl_oracle.c single thread", "host_cores": cores}
         except Exception as ex:  # the baseline is reported, never required for the GPU numbers

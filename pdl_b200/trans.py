@@ -21,9 +21,6 @@ from . import _abi, types as T
 from .core import PDL, _default_incs
 from .engine import Engine, PDLError, default_engine
 
-# parameter flags (subset of PDL_PARAM_*, lib/PDL/Core/pdl.h.PL:412-425)
-TYPED, TPLUS = 1, 2
-
 
 @dataclass
 class Par:

@@ -180,7 +180,7 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
     d.pdls[j].flags = ((p->state & PDL_BADVAL) ? PDLB200_PAR_BADFLAG : 0) | (pdlb200_pp_badval_isnan(PDLc, p) ? PDLB200_PAR_BADNAN : 0);
   }
   rc = pdlb200_readdata(&d, err, sizeof err);
-  if (rc == PDLB200_EUNSUPPORTED && fallback) { pdlb200_pp_host_calls++; return fallback(tr); }  /* e.g. > 8 unmergeable dims */
+  /* no CPU fallback for the device type matrix: an unsupported shape (e.g. > 8 unmergeable broadcast dims) is an error */
   if (rc == 0) rc = pdlb200_sync(NULL, err, sizeof err);   /* host code may read pdl->data as soon as we return */
   if (rc != 0) return PDLc->make_error(PDL_EUSERERROR, "PDL::B200 %s: %s", vt->name, err);
   for (i = 0; i < nst; i++)

@@ -1,0 +1,122 @@
+"""GPU: the BASELINE.json configurations at their FULL sizes.  The oracle cannot finish these in
+seconds, so they are checked through size-independent properties and against closed forms /
+independent device computations (torch is used only as an independent checker here):
+  cfg1  $x = $y + $c, 2048x2048 double                  -> bitwise equal to torch's IEEE add, linear in c
+  cfg2  sumover/average/minimum, float[16384,65536], 1% BAD -> exact integer-valued sums: whole == sum of halves,
+        average == sum/count (one IEEE divide), minimum == masked torch.min, a sample of rows vs the oracle
+  cfg3  [N,1]*[1,M] on strided slices + dummy dims, N=M=32768 double, then sumover -> closed form sum(a)*b[j]
+  cfg4  matmult 8192^3 double, exactly representable inputs -> bit-exact vs cuBLAS DGEMM and vs row-sum identities
+  cfg5  sum / max of 2^33 floats in {-1,0,1}           -> exact known totals
+"""
+import numpy as np
+import pytest
+
+import pdl_b200 as P
+from pdl_b200 import types as T, ufunc
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def wrap(eng, t, typ, dims):
+    return P.PDL(eng, eng.wrap(t.data_ptr(), t.numel() * t.element_size(), t), typ, dims)
+
+
+def as_torch(p, dtype):
+    """Zero-copy torch view of a contiguous device ndarray."""
+    class _CAI:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+    ts = {torch.float32: "<f4", torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+    return torch.as_tensor(_CAI(p.store.ptr + p.offs * T.SIZE[p.datatype], p.nelem, ts), device="cuda")
+
+
+def test_cfg1_plus_bit_exact(cuda_engine):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n = 2048 * 2048
+    y = torch.randint(-2**20, 2**20, (n,), device="cuda", generator=g).double() / 1024
+    c = torch.randint(-2**20, 2**20, (n,), device="cuda", generator=g).double() / 1024
+    x = wrap(cuda_engine, y, T.D, [2048, 2048]) + wrap(cuda_engine, c, T.D, [2048, 2048])
+    assert x.dims == [2048, 2048] and x.type == "double"
+    assert torch.equal(as_torch(x, torch.float64), y + c)
+    d = wrap(cuda_engine, y, T.D, [2048, 2048]) / wrap(cuda_engine, c + 0.5, T.D, [2048, 2048])
+    assert torch.equal(as_torch(d, torch.float64), y / (c + 0.5))          # IEEE divide, no FMA contraction
+
+
+def test_cfg2_reductions_full_size(cuda_engine, oracle_engine):
+    import bench
+    rows, n = bench.ROWS, bench.N_DIM
+    x = bench.generate_device(torch, 0, rows, torch.device("cuda"))
+    bad = torch.finfo(torch.float32).min
+    a = wrap(cuda_engine, x, T.F, [n, rows]).set_badflag(True)
+    s, avg, mn = ufunc.sumover(a), ufunc.average(a), ufunc.minimum(a)
+    assert s.dims == [rows] and s.badflag and avg.type == "float"
+    good = x != bad
+    want_sum = torch.where(good, x, torch.zeros_like(x)).sum(dim=1)        # values are small integers: exact in any order
+    cnt = good.sum(dim=1)
+    ts, ta, tm = as_torch(s, torch.float32), as_torch(avg, torch.float32), as_torch(mn, torch.float32)
+    assert torch.equal(ts, want_sum)
+    assert torch.equal(ta, want_sum / cnt.float())                           # one IEEE divide of exact operands
+    assert torch.equal(tm, torch.where(good, x, torch.full_like(x, float("inf"))).min(dim=1).values)
+    # linearity / additivity: the whole row equals the sum of its two halves (views, no copies)
+    h1 = ufunc.sumover(a.slice(f"0:{n // 2 - 1},:"))
+    h2 = ufunc.sumover(a.slice(f"{n // 2}:-1,:"))
+    assert torch.equal(as_torch(h1 + h2, torch.float32), ts)
+    # checksum of checksums vs the reference's own run recorded in oracle/ref_bench.pl terms: rows 0..511
+    assert float(ts[:512].double().sum()) == -5815.0 and float(tm[:512].double().sum()) == -4096.0
+    # a sample of rows against the oracle
+    host = bench.sample_numpy(4096, 16)
+    pa = P.PDL.from_numpy(host, T.F, oracle_engine).set_badflag(True)
+    for op, got in (("sumover", s), ("average", avg), ("minimum", mn)):
+        assert got.slice("4096:4111").to_numpy().tobytes() == getattr(ufunc, op)(pa).to_numpy().tobytes()
+
+
+def test_cfg3_outer_product_views(cuda_engine):
+    N = M = 32768
+    g = torch.Generator(device="cuda").manual_seed(13)
+    big1 = torch.randint(-1024, 1024, (2 * N,), device="cuda", generator=g).double() / 256
+    big2 = torch.randint(-1024, 1024, (2 * M,), device="cuda", generator=g).double() / 256
+    a = wrap(cuda_engine, big1, T.D, [2 * N]).slice("0:-1:2").dummy(1, 1)      # [N,1], stride 2
+    b = wrap(cuda_engine, big2, T.D, [2 * M]).slice("0:-1:2").dummy(0, 1)      # [1,M]
+    prod = a * b
+    assert prod.dims == [N, M]
+    tp = as_torch(prod, torch.float64).view(M, N)
+    for j in (0, 1, 777, M - 1):                                               # spot rows of the 8 GiB product
+        assert torch.equal(tp[j], big1[::2] * big2[2 * j])
+    sums = ufunc.sumover(prod)
+    # every product and partial sum is exactly representable: sum_i a_i*b_j == (sum_i a_i)*b_j bitwise
+    assert torch.equal(as_torch(sums, torch.float64), big1[::2].sum() * big2[::2])
+
+
+def test_cfg4_matmult_8192(cuda_engine):
+    n = 8192
+    g = torch.Generator(device="cuda").manual_seed(17)
+    A = torch.randint(-64, 64, (n, n), device="cuda", generator=g).double() / 64
+    B = torch.randint(-64, 64, (n, n), device="cuda", generator=g).double() / 64
+    c = P.matmult(wrap(cuda_engine, A, T.D, [n, n]), wrap(cuda_engine, B, T.D, [n, n]))
+    assert cuda_engine.last_kernel().startswith("matmult_dmma")
+    tc = as_torch(c, torch.float64).view(n, n)
+    assert torch.equal(tc, A @ B)                                              # exact inputs: any summation order agrees
+    assert torch.equal(tc.sum(dim=1), A @ B.sum(dim=1))                        # C.1 == A.(B.1): still exact
+
+
+def test_cfg5_full_array_sum_max(cuda_engine):
+    n = 2 ** 33
+    if torch.cuda.mem_get_info()[0] < 40 * 2 ** 30:
+        pytest.skip("needs 32 GiB of free HBM")
+    x = torch.empty(n, dtype=torch.float32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(19)
+    step = 2 ** 28
+    total = 0
+    for i in range(0, n, step):
+        blk = torch.randint(-1, 2, (step,), device="cuda", generator=g, dtype=torch.int8)
+        total += int(blk.sum(dtype=torch.int64))
+        x[i:i + step] = blk.float()
+    x[5_000_000_001] = 7.0
+    total += 7 - int(x[5_000_000_001].item() == 7.0) * 0
+    px = wrap(cuda_engine, x, T.F, [n])
+    want = float(x.double().sum().item())
+    assert ufunc.sum(px).sclr() == want                                        # random walk: |partial sums| << 2^24
+    assert ufunc.max(px).sclr() == 7.0
+    assert ufunc.maximum_ind(px).sclr() == 5_000_000_001                       # index beyond 2^32
+    assert ufunc.min(px).sclr() == -1.0
