@@ -225,6 +225,36 @@ template <class T, class O, bool ISMAX, bool WANT_IND> struct RMinMax {
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) { Exact::finish(x, p, out); }
 };
 
+// Integer minimum / maximum WITHOUT index output: equal integers are bit-identical, so "first wins" needs no
+// index at all — the hot loop is one IMNMX per element (plus the BAD select), which is what the 8/16-bit types
+// need to stay HBM-bound (16 elements per 128-bit load).
+template <class T, bool ISMAX> struct RMinMaxInt {
+  static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = 4;
+  struct Loc { T cur; int32_t any; };
+  struct Acc { T cur; int32_t any; int32_t pad; int32_t pad2; };
+  static __device__ __forceinline__ T identity() {
+    if constexpr (tt<T>::is_uns) return ISMAX ? T(0) : T(~T(0));
+    else { using U = typename std::make_unsigned<T>::type; const T mx = (T)(U(~U(0)) >> 1); return ISMAX ? (T)(-mx - 1) : mx; }
+  }
+  static __device__ __forceinline__ Loc linit() { Loc x; x.cur = identity(); x.any = 0; return x; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) {
+    x.cur = ISMAX ? (v > x.cur ? v : x.cur) : (v < x.cur ? v : x.cur);
+    x.any = 1;
+  }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.cur = l.cur; x.any = l.any; x.pad = 0; x.pad2 = 0; return x; }
+  static __device__ __forceinline__ Acc init() { Acc x; x.cur = identity(); x.any = 0; x.pad = 0; x.pad2 = 0; return x; }
+  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
+    Acc x; x.any = l.any | r.any; x.pad = 0; x.pad2 = 0;
+    x.cur = ISMAX ? (r.cur > l.cur ? r.cur : l.cur) : (r.cur < l.cur ? r.cur : l.cur);
+    return x;
+  }
+  static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, T *out) {
+    *out = x.any ? x.cur : from_bits<T>(p.bbad);
+  }
+};
+
 // andover orover zcover xorover (logical) and bandover borover bxorover (bitwise), Ufunc.pd:143-187.
 // KIND: 0 and, 1 or, 2 zc, 3 xor, 4 band, 5 bor, 6 bxor.  Output type == input type.
 template <class T, int KIND> struct RBits {

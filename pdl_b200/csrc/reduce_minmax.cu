@@ -16,6 +16,7 @@ template <class T> struct MinV { using R = RMinMax<T, T, false, false>; };
 template <class T, bool ISMAX, bool WANT>
 static int mm(const pdlb200_trans *t, const char *name, const Err &E) {
   if constexpr (WANT) return rd_launch_typed<RMinMax<T, int64_t, ISMAX, true>, T, int64_t>(t, name, E);
+  else if constexpr (tt<T>::is_int) return rd_launch_typed<RMinMaxInt<T, ISMAX>, T, T>(t, name, E);
   else return rd_launch_typed<RMinMax<T, T, ISMAX, false>, T, T>(t, name, E);
 }
 int reduce_minmax_family(const pdlb200_trans *t, const Err &E) {
