@@ -5,13 +5,20 @@
 //  * scan_warp_kernel: one warp per row for long rows: 32 consecutive elements per step (coalesced),
 //    Kogge-Stone scan by shuffles, carry to the next step.  Integer results are bit-exact (wrap-around
 //    add/multiply is associative); float results differ from the sequential order only in rounding.
-// A single very long row still runs on one warp (a multi-CTA look-back scan is future work).
+//  * few very long rows (a 1-D cumusumover is the common case): three passes over chunks of
+//    a multiple of SC_CHUNK elements (sized for one resident wave of warps), one warp per (row, chunk): (1) chunk totals, (2) exclusive scan of the totals
+//    per row, (3) the warp scan again with the chunk's carry-in.  3 passes of traffic instead of the
+//    ideal 2, but every SM works on the row.
 #include <cstring>
 #include "common.cuh"
 namespace pdlb200 {
 
+constexpr int64_t SC_CHUNK = 4096;
+
 struct ScPlan {
   const char *a; char *b;
+  char *carry;                  // chunked mode: one O per (row, chunk)
+  int64_t nchunks, chunk;
   int64_t n, inc_a, inc_b, nrows;
   int64_t dims[MAXD], sa[MAXD], sb[MAXD];
   uint64_t abad, bbad;
@@ -63,6 +70,17 @@ template <class O> __device__ __forceinline__ O shfl_up_t(O v, int d) {
     memcpy(&v, &u, 4); return v;
   }
 }
+template <class O> __device__ __forceinline__ O shfl_xor_t(O v, int m) {
+  if constexpr (sizeof(O) == 8) {
+    unsigned long long u; memcpy(&u, &v, 8);
+    u = __shfl_xor_sync(0xffffffffu, u, m);
+    memcpy(&v, &u, 8); return v;
+  } else {
+    unsigned u; memcpy(&u, &v, 4);
+    u = __shfl_xor_sync(0xffffffffu, u, m);
+    memcpy(&v, &u, 4); return v;
+  }
+}
 template <class O> __device__ __forceinline__ O shfl_idx_t(O v, int src) {
   if constexpr (sizeof(O) == 8) {
     unsigned long long u; memcpy(&u, &v, 8);
@@ -111,12 +129,183 @@ __global__ void __launch_bounds__(256) scan_warp_kernel(const __grid_constant__ 
   }
 }
 
+// chunked mode, pass 1 and 3.  APPLY=false: write the chunk's total (good elements only) to carry[row][chunk];
+// APPLY=true: scan the chunk starting from carry[row][chunk] (already turned into an exclusive prefix by pass 2).
+template <class T, class O, bool PROD, bool APPLY>
+__global__ void __launch_bounds__(256) scan_chunk_kernel(const __grid_constant__ ScPlan p) {
+  const T abad = from_bits<T>(p.abad);
+  const O bbad = from_bits<O>(p.bbad);
+  const O ident = PROD ? O(1) : O(0);
+  const int lane = threadIdx.x & 31;
+  const int64_t nwork = p.nrows * p.nchunks;
+  int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (; w < nwork; w += (int64_t)gridDim.x * 8) {
+    const int64_t row = w / p.nchunks, chunk = w - row * p.nchunks;
+    int64_t oa = 0, ob = 0, r = row;
+    for (int d = 0; d < p.nd; d++) {
+      const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d];
+      const int64_t i = r - q * p.dims[d];
+      oa += i * p.sa[d]; ob += i * p.sb[d]; r = q;
+    }
+    const T *pa = reinterpret_cast<const T *>(p.a) + oa;
+    O *pb = reinterpret_cast<O *>(p.b) + ob;
+    O *cw = reinterpret_cast<O *>(p.carry) + w;
+    const int64_t lo = chunk * p.chunk, hi = (lo + p.chunk < p.n) ? lo + p.chunk : p.n;
+    O carry = APPLY ? *cw : ident;
+    constexpr int VEC = 16 / sizeof(T);
+    // vector path: same-size in/out, unit strides, 16-byte aligned chunk starts (p.chunk is a multiple of SC_CHUNK, hence of every VEC)
+    const bool vec = sizeof(T) == sizeof(O) && p.inc_a == 1 && (!APPLY || p.inc_b == 1) &&
+                     (((uintptr_t)(pa + lo)) & 15) == 0 && (!APPLY || (((uintptr_t)(pb + lo)) & 15) == 0);
+    if (vec) {
+      constexpr int U = 4;                                   // 128-bit loads in flight per lane
+      const int64_t nvec = (hi - lo) / VEC;                  // full vectors; the tail goes through the scalar loop
+      const uint4 *vp = reinterpret_cast<const uint4 *>(pa + lo);
+      O tot = ident;
+      for (int64_t v0 = 0; v0 < nvec; v0 += 32 * U) {
+        Pack<T> in[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int64_t j = v0 + u * 32 + lane; if (j < nvec) in[u].q = vp[j]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int64_t j = v0 + u * 32 + lane;
+          const bool inr = j < nvec;
+          O x[VEC]; bool bd[VEC];
+          O run = ident;
+#pragma unroll
+          for (int k = 0; k < VEC; k++) {
+            const T v = inr ? in[u].e[k] : T(0);
+            bd[k] = inr && p.badmode && is_bad(v, abad, p.abadnan != 0);
+            if (inr && !bd[k]) run = scan_op<O, PROD>(run, (O)v);
+            x[k] = run;                                      // inclusive scan inside the lane's vector
+          }
+          if (!APPLY) { tot = scan_op<O, PROD>(tot, run); continue; }
+          O pre = run;                                       // exclusive scan of the lane totals across the warp
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const O y = shfl_up_t(pre, d);
+            if (lane >= d) pre = scan_op<O, PROD>(y, pre);
+          }
+          const O warp_total = shfl_idx_t(pre, 31);
+          O excl = shfl_up_t(pre, 1);
+          if (lane == 0) excl = ident;
+          const O base = scan_op<O, PROD>(carry, excl);
+          if (inr) {
+            Pack<O> out;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) out.e[k] = bd[k] ? bbad : scan_op<O, PROD>(base, x[k]);
+            reinterpret_cast<uint4 *>(pb + lo)[j] = out.q;
+          }
+          carry = scan_op<O, PROD>(carry, warp_total);
+        }
+      }
+      if (!APPLY) {
+        for (int64_t n = lo + nvec * VEC + lane; n < hi; n += 32) {
+          const T v = pa[n];
+          if (!(p.badmode && is_bad(v, abad, p.abadnan != 0))) tot = scan_op<O, PROD>(tot, (O)v);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) tot = scan_op<O, PROD>(tot, shfl_xor_t(tot, d));
+        if (lane == 0) *cw = tot;
+      } else {
+        for (int64_t n0 = lo + nvec * VEC; n0 < hi; n0 += 32) {
+          const int64_t n = n0 + lane;
+          const bool in1 = n < hi;
+          const T v = in1 ? pa[n] : T(0);
+          const bool bad = in1 && p.badmode && is_bad(v, abad, p.abadnan != 0);
+          O x = (in1 && !bad) ? (O)v : ident;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const O y = shfl_up_t(x, d); if (lane >= d) x = scan_op<O, PROD>(y, x); }
+          const O res = scan_op<O, PROD>(carry, x);
+          if (in1) pb[n] = bad ? bbad : res;
+          carry = shfl_idx_t(res, 31);
+        }
+      }
+      continue;
+    }
+    if (!APPLY) {
+      O tot = ident;
+#pragma unroll 4
+      for (int64_t n = lo + lane; n < hi; n += 32) {
+        const T v = pa[n * p.inc_a];
+        if (!(p.badmode && is_bad(v, abad, p.abadnan != 0))) tot = scan_op<O, PROD>(tot, (O)v);
+      }
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) tot = scan_op<O, PROD>(tot, shfl_xor_t(tot, d));
+      if (lane == 0) *cw = tot;
+    } else {
+      for (int64_t n0 = lo; n0 < hi; n0 += 32) {
+        const int64_t n = n0 + lane;
+        const bool in = n < hi;
+        const T v = in ? pa[n * p.inc_a] : T(0);
+        const bool bad = in && p.badmode && is_bad(v, abad, p.abadnan != 0);
+        O x = (in && !bad) ? (O)v : ident;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const O y = shfl_up_t(x, d);
+          if (lane >= d) x = scan_op<O, PROD>(y, x);
+        }
+        const O res = scan_op<O, PROD>(carry, x);
+        if (in) pb[n * p.inc_b] = bad ? bbad : res;
+        carry = shfl_idx_t(res, 31);
+      }
+    }
+  }
+}
+
+// chunked mode, pass 2: carry[row][c] = op over totals of chunks < c (one warp per row, 4 loads in flight per lane)
+template <class O, bool PROD>
+__global__ void __launch_bounds__(256) scan_chunk_prefix_kernel(const __grid_constant__ ScPlan p) {
+  const O ident = PROD ? O(1) : O(0);
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.nrows; row += (int64_t)gridDim.x * 8) {
+    O *c = reinterpret_cast<O *>(p.carry) + row * p.nchunks;
+    O run = ident;
+    for (int64_t k0 = 0; k0 < p.nchunks; k0 += 128) {
+      O t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int64_t k = k0 + u * 32 + lane; t[u] = k < p.nchunks ? c[k] : ident; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int64_t k = k0 + u * 32 + lane;
+        O x = t[u];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const O y = shfl_up_t(x, d); if (lane >= d) x = scan_op<O, PROD>(y, x); }
+        O excl = shfl_up_t(x, 1);
+        if (lane == 0) excl = ident;
+        if (k < p.nchunks) c[k] = scan_op<O, PROD>(run, excl);
+        run = scan_op<O, PROD>(run, shfl_idx_t(x, 31));
+      }
+    }
+  }
+}
+
 template <class T, class O, bool PROD>
 static int scan_go(const ScPlan &p, cudaStream_t s, const char *name, const Err &E) {
   const int64_t cap = (int64_t)sm_count() * 8;
   // long rows that are not laid out column-wise: one warp per row
   const bool column = (p.nd >= 1) && (p.sa[0] == 1 || p.sa[0] == -1) && p.inc_a != 1 && p.dims[0] >= 32;
-  if (p.n >= 128 && !column) {
+  // chunk length: a multiple of SC_CHUNK giving about one resident wave of warps (64 per SM) over all rows
+  int64_t want = cap * 8 / (p.nrows > 0 ? p.nrows : 1);
+  if (want < 1) want = 1;
+  int64_t chunk = (p.n + want - 1) / want;
+  chunk = (chunk + SC_CHUNK - 1) / SC_CHUNK * SC_CHUNK;
+  if (chunk < SC_CHUNK) chunk = SC_CHUNK;
+  const int64_t nchunks = (p.n + chunk - 1) / chunk;
+  if (!column && nchunks >= 4 && p.nrows < cap && p.nrows * nchunks <= (1ll << 26)) {
+    // few long rows: cut them into chunks so that every SM takes part
+    ScPlan q = p;
+    q.nchunks = nchunks;
+    q.chunk = chunk;
+    q.carry = (char *)scratch((size_t)(p.nrows * nchunks) * sizeof(O), s);
+    if (!q.carry) return E.fail(PDLB200_ECUDA, "%s: cannot allocate scan scratch", name);
+    int64_t g = (p.nrows * nchunks + 7) / 8;
+    if (g > cap * 4) g = cap * 4;
+    scan_chunk_kernel<T, O, PROD, false><<<(int)g, 256, 0, s>>>(q);
+    int64_t g2 = (p.nrows + 7) / 8;
+    scan_chunk_prefix_kernel<O, PROD><<<(int)g2, 256, 0, s>>>(q);
+    scan_chunk_kernel<T, O, PROD, true><<<(int)g, 256, 0, s>>>(q);
+    note_launch(name); note_launch(name);
+  } else if (p.n >= 128 && !column) {
     int64_t g = (p.nrows + 7) / 8;
     if (g > cap) g = cap;
     scan_warp_kernel<T, O, PROD><<<(int)g, 256, 0, s>>>(p);

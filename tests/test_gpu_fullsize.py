@@ -120,3 +120,27 @@ def test_cfg5_full_array_sum_max(cuda_engine):
     assert ufunc.max(px).sclr() == 7.0
     assert ufunc.maximum_ind(px).sclr() == 5_000_000_001                       # index beyond 2^32
     assert ufunc.min(px).sclr() == -1.0
+
+
+def test_long_row_scan_chunked(cuda_engine):
+    """cumusumover / cumuprodover over one very long row (the chunked three-pass scan, chunk > 4096):
+    integer-valued floats make every partial sum exact, so any association order must agree bitwise."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    n = 2**27 + 12345
+    x = torch.randint(-8, 9, (n,), device="cuda", generator=g).float()
+    got = as_torch(ufunc.cumusumover(wrap(cuda_engine, x, T.F, [n])), torch.float32)
+    assert torch.equal(got, torch.cumsum(x.double(), 0).float())
+    # two rows with 1% BAD: BAD elements give BAD out and do not contribute
+    n2 = 2**25 + 3
+    y = torch.randint(-8, 9, (2 * n2,), device="cuda", generator=g).float()
+    bad = torch.rand(2 * n2, device="cuda", generator=g) < 0.01
+    y[bad] = -9999.0
+    py = wrap(cuda_engine, y, T.F, [n2, 2])
+    py.set_badvalue(-9999.0)
+    py.badflag = True
+    out = ufunc.cumusumover(py)
+    assert out.badflag
+    got = as_torch(out, torch.float32).view(2, n2)
+    want = torch.cumsum(torch.where(bad, torch.zeros_like(y), y).view(2, n2).double(), 1).float()
+    want[bad.view(2, n2)] = float(out.badvalue)
+    assert torch.equal(got, want)

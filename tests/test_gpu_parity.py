@@ -252,7 +252,7 @@ def test_matmult_default_path_double(engines):
 @pytest.mark.parametrize("t", [T.B, T.S, T.L, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
 def test_scans(engines, t):
     rng = np.random.default_rng(1500 + t)
-    for (n, rows) in [(5, 3000), (1000, 37), (40_001, 2)]:          # thread-per-row and warp-per-row kernels
+    for (n, rows) in [(5, 3000), (1000, 37), (40_001, 2), (300_007, 1)]:   # thread-per-row, warp-per-row, chunked
         a = rand_array(rng, t, (rows, n), "exact" if t in (T.F, T.D) else "mixed")
         for bad in (False, True):
             src = a.copy()
