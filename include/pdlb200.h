@@ -34,7 +34,7 @@ extern "C" {
 #define PDLB200_API
 #endif
 
-#define PDLB200_ABI_VERSION 1
+#define PDLB200_ABI_VERSION 2
 
 /* Element types: numeric values are PDL's own pdl_datatypes enum
  * (lib/PDL/Types.pm:27-255, order is significant for promotion).
@@ -76,6 +76,19 @@ enum {
   PDLB200_OP_CONVERT = 61,
   /* ipow, lib/PDL/Ops.pd:443-476 : a(); longlong b(); [o]ans() — exponentiation by squaring */
   PDLB200_OP_IPOW = 62,
+  /* bad-value producers/consumers either side of the path, lib/PDL/Bad.pd:343-416,584-905.
+   * isbad/isgood/isnan: a(); int [o]b().  setbadif: a(); int mask(); [o]b().  setvaltobad/setbadtoval:
+   * a(); [o]b() with the OtherPars double in `param`.  set{nan,inf,nonfinite}tobad, setbadtonan: a(); [o]b(),
+   * floating point only.  badmask: a(); b(); [o]c().  copybad: a(); mask(); [o]b(). */
+  PDLB200_OP_ISBAD = 63, PDLB200_OP_ISGOOD, PDLB200_OP_ISNAN, PDLB200_OP_SETBADIF, PDLB200_OP_SETVALTOBAD,
+  PDLB200_OP_SETNANTOBAD, PDLB200_OP_SETINFTOBAD, PDLB200_OP_SETNONFINITETOBAD, PDLB200_OP_SETBADTONAN,
+  PDLB200_OP_SETBADTOVAL, PDLB200_OP_BADMASK, PDLB200_OP_COPYBAD,
+  /* axisvalues, lib/PDL/Primitive.pd:1468-1474 : i(n); [o]a(n) — a = n; the body of sequence/xvals/yvals/zvals
+   * (lib/PDL/Basic.pm:117-129,479-485).  n_size = ind[0], inc_a_n = rinc[1] (rinc[0] is i's, never read). */
+  PDLB200_OP_AXISVALUES = 75,
+  /* inner, lib/PDL/Primitive.pd:48-70 : a(n); b(n); [o]c() — c = sum_n a*b; n_size = ind[0],
+   * inc_a_n = rinc[0], inc_b_n = rinc[1].  Any BAD element in the row makes c BAD. */
+  PDLB200_OP_INNER = 76,
   PDLB200_OP__END
 };
 
@@ -116,6 +129,11 @@ typedef struct pdlb200_trans {
   int64_t rinc[8];
   pdlb200_par pdls[PDLB200_MAXPDLS];                /* inputs first, then outputs */
   void   *stream;    /* cudaStream_t to launch on; NULL = legacy default stream */
+  double  param;     /* the OtherPars double of setvaltobad (value) / setbadtoval (newval): $COMP(...) */
+  /* set{nan,inf,nonfinite}tobad mark their output BAD only if they wrote a BAD value (`if (flag)
+   * $PDLSTATESETBAD(b)`, lib/PDL/Bad.pd:695-707).  Those three ops REQUIRE a host pointer here; the
+   * call synchronises the stream and stores 1/0.  Ignored by every other op. */
+  int32_t *anybad;
 } pdlb200_trans;
 
 /* Return codes.  Non-zero => `err` (if given) holds a NUL-terminated message the

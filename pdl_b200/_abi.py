@@ -40,6 +40,8 @@ class Trans(C.Structure):
         ("rinc", C.c_int64 * 8),
         ("pdls", Par * MAXPDLS),
         ("stream", C.c_void_p),
+        ("param", C.c_double),
+        ("anybad", C.POINTER(C.c_int32)),
     ]
 
 
@@ -58,7 +60,11 @@ OPS = {
     "zcover": 44, "xorover": 45, "bxorover": 46, "nbadover": 47, "ngoodover": 48,
     "cumusumover": 50, "cumuprodover": 51, "dcumusumover": 52, "dcumuprodover": 53,
     "matmult": 60, "converttype": 61, "ipow": 62,
+    "isbad": 63, "isgood": 64, "isnan": 65, "setbadif": 66, "setvaltobad": 67,
+    "setnantobad": 68, "setinftobad": 69, "setnonfinitetobad": 70, "setbadtonan": 71,
+    "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76,
 }
+ABI_VERSION = 2
 
 # every symbol include/pdlb200.h declares (tests check the .so exports them all)
 SYMBOLS = [

@@ -93,6 +93,11 @@ static void init_names() {
   N(PDLB200_OP_CUMUSUMOVER, "cumusumover") N(PDLB200_OP_CUMUPRODOVER, "cumuprodover")
   N(PDLB200_OP_DCUMUSUMOVER, "dcumusumover") N(PDLB200_OP_DCUMUPRODOVER, "dcumuprodover")
   N(PDLB200_OP_MATMULT, "matmult") N(PDLB200_OP_CONVERT, "converttype") N(PDLB200_OP_IPOW, "ipow")
+  N(PDLB200_OP_ISBAD, "isbad") N(PDLB200_OP_ISGOOD, "isgood") N(PDLB200_OP_ISNAN, "isnan")
+  N(PDLB200_OP_SETBADIF, "setbadif") N(PDLB200_OP_SETVALTOBAD, "setvaltobad") N(PDLB200_OP_SETNANTOBAD, "setnantobad")
+  N(PDLB200_OP_SETINFTOBAD, "setinftobad") N(PDLB200_OP_SETNONFINITETOBAD, "setnonfinitetobad")
+  N(PDLB200_OP_SETBADTONAN, "setbadtonan") N(PDLB200_OP_SETBADTOVAL, "setbadtoval") N(PDLB200_OP_BADMASK, "badmask")
+  N(PDLB200_OP_COPYBAD, "copybad") N(PDLB200_OP_AXISVALUES, "axisvalues") N(PDLB200_OP_INNER, "inner")
 #undef N
 }
 
@@ -130,6 +135,8 @@ int launch_elementwise(const pdlb200_trans *t, const Err &E) {
   if (op <= PDLB200_OP_ABS2) return ew_unary(t, E);
   if (op == PDLB200_OP_CONVERT) return launch_convert(t, E);
   if (op == PDLB200_OP_IPOW) return launch_ipow(t, E);
+  if (op >= PDLB200_OP_ISBAD && op <= PDLB200_OP_COPYBAD) return launch_badops(t, E);
+  if (op == PDLB200_OP_AXISVALUES) return launch_axisvalues(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not an elementwise op", pdlb200_op_name(op));
 }
 
@@ -179,6 +186,7 @@ int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
   if (int rc = validate(t, E)) return rc;
   if (t->op >= PDLB200_OP_CUMUSUMOVER && t->op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (t->op >= PDLB200_OP_SUMOVER && t->op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
+  if (t->op == PDLB200_OP_INNER) return launch_inner(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
 }
 int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
@@ -191,7 +199,9 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   Err E{err, errlen};
   if (int rc = validate(t, E)) return rc;
   const int op = t->op;
-  if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT || op == PDLB200_OP_IPOW) return launch_elementwise(t, E);
+  if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT || op == PDLB200_OP_IPOW ||
+      (op >= PDLB200_OP_ISBAD && op <= PDLB200_OP_AXISVALUES)) return launch_elementwise(t, E);
+  if (op == PDLB200_OP_INNER) return launch_inner(t, E);
   if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);

@@ -106,6 +106,9 @@ void collapse_dims(const pdlb200_trans *t, Collapsed *c);
 int launch_elementwise(const pdlb200_trans *t, const Err &E);
 int launch_convert(const pdlb200_trans *t, const Err &E);
 int launch_ipow(const pdlb200_trans *t, const Err &E);
+int launch_badops(const pdlb200_trans *t, const Err &E);
+int launch_axisvalues(const pdlb200_trans *t, const Err &E);
+int launch_inner(const pdlb200_trans *t, const Err &E);
 int launch_reduce(const pdlb200_trans *t, const Err &E);
 int launch_scan(const pdlb200_trans *t, const Err &E);
 int launch_matmult(const pdlb200_trans *t, const Err &E);

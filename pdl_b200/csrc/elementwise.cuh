@@ -15,6 +15,7 @@
 // dims) are gathered element-wise into the same register image, so vaffine views
 // are read in place and never materialised.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace pdlb200 {
@@ -35,7 +36,41 @@ struct EwPlan {
   int badnan[3];
   int badchk[3];               // test this input for BAD (state flag for biop; always for bifunc/ufunc)
   int vec[3];                  // 128-bit access allowed on full units
+  uint64_t param;              // bad-aware ops: bits of the OtherPars value, already cast to the element type
+  int *flag;                   // bad-aware ops with a data-dependent output badflag: device word, set to 1
 };
+
+// Element types may differ per operand (convert: TI -> TO; setbadif: int mask): a unit is as many
+// elements as fit 16 bytes of the WIDEST type involved.
+template <class TI, class TO, class TB> constexpr int ew_vec() {
+  size_t w = sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO);
+  if (sizeof(TB) > w) w = sizeof(TB);
+  return (int)(16 / w);
+}
+
+// Functor protocols.  Plain ops: `TO f<TI,TO>(TI a, TI b)`; the kernel handles BAD (any BAD input -> BAD out).
+// Bad-aware ops (lib/PDL/Bad.pd) declare `static constexpr bool kBadAware = true` and get the BAD tests as
+// arguments: `TO g<TI,TB,TO>(TI a, bool abad, TB b, bool bbad, TO cbad, uint64_t param, int &flag)`.
+template <class Op, class = void> struct op_badaware : std::false_type {};
+template <class Op> struct op_badaware<Op, std::void_t<decltype(Op::kBadAware)>> : std::true_type {};
+
+template <class Op, class TI, class TB, class TO, bool BAD, int NIN>
+__device__ __forceinline__ TO ew_apply(const EwPlan &p, TI a, TB b, TI abad, TB bbad, TO cbad, int &flag) {
+  bool ba = false, bb = false;
+  if constexpr (BAD) {
+    ba = p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0);
+    if (NIN > 1) bb = p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0);
+  }
+  if constexpr (op_badaware<Op>::value) {
+    return Op::template g<TI, TB, TO>(a, ba, b, bb, cbad, p.param, flag);
+  } else {
+    const TO r = Op::template f<TI, TO>(a, b);
+    return (ba || bb) ? cbad : r;
+  }
+}
+template <class Op> __device__ __forceinline__ void ew_publish_flag(const EwPlan &p, int flag) {
+  if constexpr (op_badaware<Op>::value) { if (flag && p.flag) atomicOr(p.flag, 1); }
+}
 
 // Vector access moves VEC elements = VEC*sizeof(T) bytes (16 for same-type ops;
 // 8/4/2/1 for the narrow side of a convert).
@@ -76,20 +111,22 @@ __device__ __forceinline__ void ew_store(const Pack<T> &r, char *base, int64_t o
 
 // Op: struct with `template<class T> static __device__ T f(T a, T b)`.
 // TI = input element type, TO = output element type (differ only for convert).
-template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
+template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL, class TB = TI>
 __global__ void __launch_bounds__(EW_THREADS)
 ew_kernel(const __grid_constant__ EwPlan p) {
-  constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
+  constexpr int VEC = ew_vec<TI, TO, TB>();
+  int flag = 0;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const TI abad = from_bits<TI>(p.bad[0]);
-  const TI bbad = from_bits<TI>(p.bad[NIN > 1 ? 1 : 0]);
+  const TB bbad = from_bits<TB>(p.bad[NIN > 1 ? 1 : 0]);
   const TO cbad = from_bits<TO>(p.bad[NIN]);
 
   for (int64_t u0 = tid; u0 < p.n_units; u0 += nthreads * UNROLL) {
     // Pack<> is sized for 16 bytes of the WIDER type; with mixed widths (convert)
     // the narrower side simply uses the first VEC lanes of its image.
-    Pack<TI> ra[UNROLL], rb[UNROLL];
+    Pack<TI> ra[UNROLL];
+    Pack<TB> rb[UNROLL];
     int64_t oc[UNROLL];
     int cnt[UNROLL];
 #pragma unroll
@@ -119,7 +156,7 @@ ew_kernel(const __grid_constant__ EwPlan p) {
         cnt[j] = left < VEC ? (int)left : VEC;
         oc[j] = o;
         ew_load<TI, VEC>(ra[j], p.ptr[0], oa, p.st[0][0], p.vec[0], cnt[j]);
-        if (NIN > 1) ew_load<TI, VEC>(rb[j], p.ptr[1], ob, p.st[1][0], p.vec[1], cnt[j]);
+        if (NIN > 1) ew_load<TB, VEC>(rb[j], p.ptr[1], ob, p.st[1][0], p.vec[1], cnt[j]);
       }
     }
 #pragma unroll
@@ -129,19 +166,14 @@ ew_kernel(const __grid_constant__ EwPlan p) {
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
           const TI a = ra[j].e[k];
-          const TI b = (NIN > 1) ? rb[j].e[k] : TI(0);
-          bool bad = false;
-          if constexpr (BAD) {
-            bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
-            if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
-          }
-          const TO r = Op::template f<TI, TO>(a, b);
-          rc.e[k] = bad ? cbad : r;
+          const TB b = (NIN > 1) ? rb[j].e[k] : TB(0);
+          rc.e[k] = ew_apply<Op, TI, TB, TO, BAD, NIN>(p, a, b, abad, bbad, cbad, flag);
         }
         ew_store<TO, VEC>(rc, p.ptr[NIN], oc[j], p.st[NIN][0], p.vec[NIN], cnt[j]);
       }
     }
   }
+  ew_publish_flag<Op>(p, flag);
 }
 
 // ---- tile kernel: the fast path --------------------------------------------------------------
@@ -165,34 +197,29 @@ __device__ __forceinline__ void ew_load_full(Pack<T> &r, const T *p, int64_t st0
   for (int k = 0; k < VEC; k++) r.e[k] = p[k * st0];
 }
 
-template <class Op, class TI, class TO, bool BAD, int NIN, int VEC>
-__device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI> &ra, const Pack<TI> &rb, TO *dst, int64_t sc0,
-                                                 int cnt, TI abad, TI bbad, TO cbad) {
+template <class Op, class TI, class TO, bool BAD, int NIN, int VEC, class TB>
+__device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI> &ra, const Pack<TB> &rb, TO *dst, int64_t sc0,
+                                                 int cnt, TI abad, TB bbad, TO cbad, int &flag) {
   Pack<TO> rc;
 #pragma unroll
   for (int k = 0; k < VEC; k++) {
     const TI a = ra.e[k];
-    const TI b = (NIN > 1) ? rb.e[k] : TI(0);
-    bool bad = false;
-    if constexpr (BAD) {
-      bad = (p.badchk[0] && is_bad(a, abad, p.badnan[0] != 0));
-      if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(b, bbad, p.badnan[1] != 0));
-    }
-    const TO r = Op::template f<TI, TO>(a, b);
-    rc.e[k] = bad ? cbad : r;
+    const TB b = (NIN > 1) ? rb.e[k] : TB(0);
+    rc.e[k] = ew_apply<Op, TI, TB, TO, BAD, NIN>(p, a, b, abad, bbad, cbad, flag);
   }
   ew_store<TO, VEC>(rc, reinterpret_cast<char *>(dst), 0, sc0, p.vec[NIN], cnt);
 }
 
 // 64 registers (4 CTAs/SM) for the good-mode bodies; the BAD bodies carry the extra compares/selects and
 // get 80 (3 CTAs/SM) rather than spilling inside the hot loop.
-template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL>
+template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL, class TB = TI>
 __global__ void __launch_bounds__(EW_THREADS, BAD ? 3 : 4)
 ew_tile_kernel(const __grid_constant__ EwPlan p) {
-  constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
+  constexpr int VEC = ew_vec<TI, TO, TB>();
   constexpr int64_t TILE = (int64_t)EW_THREADS * UNROLL * VEC;
+  int flag = 0;
   const TI abad = from_bits<TI>(p.bad[0]);
-  const TI bbad = from_bits<TI>(p.bad[NIN > 1 ? 1 : 0]);
+  const TB bbad = from_bits<TB>(p.bad[NIN > 1 ? 1 : 0]);
   const TO cbad = from_bits<TO>(p.bad[NIN]);
   const int64_t tpr = p.vpr, ipr = p.ipr, nitems = p.n_units;
   const int64_t sa0 = p.st[0][0], sb0 = (NIN > 1) ? p.st[1][0] : 0, sc0 = p.st[NIN][0];
@@ -230,30 +257,31 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
     const int64_t seg1 = (seg0 + p.grp < tpr) ? seg0 + p.grp : tpr;
     int64_t i_first = seg0 * TILE + (int64_t)threadIdx.x * VEC;   // this thread's first position in the row
     const TI *pa = reinterpret_cast<const TI *>(p.ptr[0]) + oa + i_first * sa0;
-    const TI *pb = reinterpret_cast<const TI *>(p.ptr[NIN > 1 ? 1 : 0]) + ob + i_first * sb0;
+    const TB *pb = reinterpret_cast<const TB *>(p.ptr[NIN > 1 ? 1 : 0]) + ob + i_first * sb0;
     TO *pc = reinterpret_cast<TO *>(p.ptr[NIN]) + oc + i_first * sc0;
 
     for (int64_t seg = seg0; seg < seg1; seg++, i_first += TILE, pa += UNROLL * ja, pb += UNROLL * jb, pc += UNROLL * jc) {
       if ((seg + 1) * TILE <= p.dims[0]) {
         // full tile: no bounds checks; all loads of the tile are issued before the first use.  Inputs that
         // are constant along dim 1 are loaded for the first row of the block only.
-        Pack<TI> ra[UNROLL], rb[UNROLL];
+        Pack<TI> ra[UNROLL];
+        Pack<TB> rb[UNROLL];
         for (int rr = 0; rr < rows_here; rr++) {
           const TI *qa = pa + rr * sa1;
-          const TI *qb = pb + rr * sb1;
+          const TB *qb = pb + rr * sb1;
           if (rr == 0 || !a_inv) {
             const TI bca = a_bc ? *qa : TI(0);    // dummy along dim 0: one load per row
 #pragma unroll
             for (int j = 0; j < UNROLL; j++) ew_load_full<TI, VEC>(ra[j], qa + j * ja, sa0, p.vec[0], bca, a_bc);
           }
           if (NIN > 1 && (rr == 0 || !b_inv)) {
-            const TI bcb = b_bc ? *qb : TI(0);
+            const TB bcb = b_bc ? *qb : TB(0);
 #pragma unroll
-            for (int j = 0; j < UNROLL; j++) ew_load_full<TI, VEC>(rb[j], qb + j * jb, sb0, p.vec[1], bcb, b_bc);
+            for (int j = 0; j < UNROLL; j++) ew_load_full<TB, VEC>(rb[j], qb + j * jb, sb0, p.vec[1], bcb, b_bc);
           }
 #pragma unroll
           for (int j = 0; j < UNROLL; j++)
-            ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra[j], rb[NIN > 1 ? j : 0], pc + rr * sc1 + j * jc, sc0, VEC, abad, bbad, cbad);
+            ew_compute_store<Op, TI, TO, BAD, NIN, VEC, TB>(p, ra[j], rb[NIN > 1 ? j : 0], pc + rr * sc1 + j * jc, sc0, VEC, abad, bbad, cbad, flag);
         }
       } else {
         // last (partial) tile of a row: one unit at a time
@@ -263,30 +291,34 @@ ew_tile_kernel(const __grid_constant__ EwPlan p) {
             const int64_t left = p.dims[0] - i_first - (int64_t)j * EW_THREADS * VEC;
             if (left <= 0) break;
             const int cnt = left < VEC ? (int)left : VEC;
-            Pack<TI> ra, rb;
+            Pack<TI> ra;
+            Pack<TB> rb;
             ew_load<TI, VEC>(ra, reinterpret_cast<const char *>(pa + rr * sa1 + j * ja), 0, sa0, p.vec[0], cnt);
-            if (NIN > 1) ew_load<TI, VEC>(rb, reinterpret_cast<const char *>(pb + rr * sb1 + j * jb), 0, sb0, p.vec[1], cnt);
-            ew_compute_store<Op, TI, TO, BAD, NIN, VEC>(p, ra, rb, pc + rr * sc1 + j * jc, sc0, cnt, abad, bbad, cbad);
+            if (NIN > 1) ew_load<TB, VEC>(rb, reinterpret_cast<const char *>(pb + rr * sb1 + j * jb), 0, sb0, p.vec[1], cnt);
+            ew_compute_store<Op, TI, TO, BAD, NIN, VEC, TB>(p, ra, rb, pc + rr * sc1 + j * jc, sc0, cnt, abad, bbad, cbad, flag);
           }
         }
       }
     }
   }
+  ew_publish_flag<Op>(p, flag);
 }
 
 // host side: build the plan and launch (ew_plan.cu)
 int ew_build_plan(const pdlb200_trans *t, int nin, size_t in_size, size_t out_size,
-                  bool state_checked_bad, EwPlan *p, const Err &E);
+                  bool state_checked_bad, EwPlan *p, const Err &E, size_t b_size = 0);
 int ew_grid(int64_t n_units, int unroll, const void *kernel);
 
-template <class Op, class TI, class TO, int NIN>
-int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *name, const Err &E) {
+template <class Op, class TI, class TO, int NIN, class TB = TI>
+int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *name, const Err &E,
+                    uint64_t param = 0, int *flag = nullptr) {
   EwPlan p;
-  int rc = ew_build_plan(t, NIN, sizeof(TI), sizeof(TO), state_checked_bad, &p, E);
+  int rc = ew_build_plan(t, NIN, sizeof(TI), sizeof(TO), state_checked_bad, &p, E, sizeof(TB));
   if (rc) return rc;
   if (p.n_units == 0) return PDLB200_OK;  // empty broadcast: the loop body never runs
+  p.param = param; p.flag = flag;
   cudaStream_t s = (cudaStream_t)t->stream;
-  constexpr int VEC = 16 / (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
+  constexpr int VEC = ew_vec<TI, TO, TB>();
   constexpr int TU = 4;                                    // units per thread per tile
   constexpr int64_t TILE = (int64_t)EW_THREADS * TU * VEC;
   if (p.nd == 1 || p.dims[0] >= TILE / 2) {
@@ -317,15 +349,15 @@ int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *
     p.vpr = tpr; p.n_units = p.ipr * rowblocks;
     const int64_t cap = (int64_t)sm_count() * 32;
     const int grid = (int)(p.n_units < cap ? p.n_units : cap);
-    if (t->bvalflag) ew_tile_kernel<Op, TI, TO, true, NIN, TU><<<grid, EW_THREADS, 0, s>>>(p);
-    else ew_tile_kernel<Op, TI, TO, false, NIN, TU><<<grid, EW_THREADS, 0, s>>>(p);
+    if (t->bvalflag) ew_tile_kernel<Op, TI, TO, true, NIN, TU, TB><<<grid, EW_THREADS, 0, s>>>(p);
+    else ew_tile_kernel<Op, TI, TO, false, NIN, TU, TB><<<grid, EW_THREADS, 0, s>>>(p);
   } else {
     constexpr int UNROLL = 2;
     if (t->bvalflag) {
-      auto k = ew_kernel<Op, TI, TO, true, NIN, UNROLL>;
+      auto k = ew_kernel<Op, TI, TO, true, NIN, UNROLL, TB>;
       k<<<ew_grid(p.n_units, UNROLL, (const void *)k), EW_THREADS, 0, s>>>(p);
     } else {
-      auto k = ew_kernel<Op, TI, TO, false, NIN, UNROLL>;
+      auto k = ew_kernel<Op, TI, TO, false, NIN, UNROLL, TB>;
       k<<<ew_grid(p.n_units, UNROLL, (const void *)k), EW_THREADS, 0, s>>>(p);
     }
   }

@@ -43,7 +43,8 @@ void collapse_dims(const pdlb200_trans *t, Collapsed *c) {
 }
 
 int ew_build_plan(const pdlb200_trans *t, int nin, size_t in_size, size_t out_size,
-                  bool state_checked_bad, EwPlan *p, const Err &E) {
+                  bool state_checked_bad, EwPlan *p, const Err &E, size_t b_size) {
+  if (b_size == 0) b_size = in_size;
   if (t->npdls != nin + 1)
     return E.fail(PDLB200_EINVAL, "%s: expected %d parameters, got %d", pdlb200_op_name(t->op), nin + 1, t->npdls);
   Collapsed c;
@@ -52,13 +53,14 @@ int ew_build_plan(const pdlb200_trans *t, int nin, size_t in_size, size_t out_si
     return E.fail(PDLB200_EUNSUPPORTED, "%s: %d non-mergeable broadcast dims exceed the device walker's %d",
                   pdlb200_op_name(t->op), c.nd, MAXD);
   memset(p, 0, sizeof *p);
-  const size_t wide = in_size > out_size ? in_size : out_size;
+  size_t wide = in_size > out_size ? in_size : out_size;
+  if (nin > 1 && b_size > wide) wide = b_size;
   const int VEC = (int)(16 / wide);
   p->nd = c.nd;
   for (int d = 0; d < c.nd; d++) p->dims[d] = c.dims[d];
   for (int k = 0; k <= nin; k++) {
     const pdlb200_par &par = t->pdls[k];
-    const size_t sz = k < nin ? in_size : out_size;
+    const size_t sz = k == nin ? out_size : (k == 1 ? b_size : in_size);
     if (c.total > 0 && !par.data)
       return E.fail(PDLB200_EINVAL, "%s: parameter %d got NULL data", pdlb200_op_name(t->op), k);
     p->ptr[k] = (char *)par.data + par.offs * (int64_t)sz;

@@ -59,7 +59,7 @@ class CudaEngine(Engine):
 
     def __init__(self, device: int | None = None):
         self.lib = _abi.load()  # raises LibraryMissing if the extension is not built
-        if self.lib.pdlb200_abi_version() != 1:
+        if self.lib.pdlb200_abi_version() != _abi.ABI_VERSION:
             raise PDLError("libpdlb200.so ABI version mismatch")
         n = self.lib.pdlb200_device_count()
         if n <= 0:

@@ -27,4 +27,11 @@ def matmult(x, y, c=None) -> PDL:
     return run_op("matmult", [x, y], [c])[0]
 
 
-__all__ = ["matmult"]
+def inner(a, b, c=None) -> PDL:
+    """PDL::inner(a(n); b(n); [o]c()) — lib/PDL/Primitive.pd:48-70: c = sum_n a*b in ONE launch; the fused
+    form of `($a * $b)->sumover` (the product ndarray never exists)."""
+    a = as_pdl(a)
+    return run_op("inner", [a, as_pdl(b, a.engine)], [c])[0]
+
+
+__all__ = ["matmult", "inner"]

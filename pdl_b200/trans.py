@@ -48,6 +48,12 @@ _A, _R, _I = T.ALL, T.REAL, T.INTEGER
 # Ops.pd:8-9,321,332: [@$C, @$F] with D last so that non-float input falls back to double
 _CF = T.COMPLEX + T.FLOATING
 _F = T.FLOATING
+_AF = (T.F, T.LD) + T.COMPLEX + (T.D,)
+
+# what the op's Code does to the output state after make_trans_mutual propagated the input flags
+_STATE_SETBAD = ("setbadif", "setvaltobad")                       # $PDLSTATESETBAD(b), unconditionally
+_STATE_SETGOOD = ("setbadtonan", "setbadtoval", "badmask")        # $PDLSTATESETGOOD(b)
+_STATE_IFFLAG = ("setnantobad", "setinftobad", "setnonfinitetobad")  # if (flag) $PDLSTATESETBAD(b)
 
 
 def _bi(name, gentypes, kind="biop"):
@@ -93,6 +99,22 @@ SPECS = {s.name: s for s in [
     # ipow, lib/PDL/Ops.pd:443-476: GenericTypes [P Q, non-integer types with D last]
     OpSpec("ipow", [Par("a"), Par("b", typed=T.LL), Par("ans", out=True)],
            (T.ULL, T.LL, T.F, T.LD, T.CF, T.CD, T.CLD, T.D), "ufunc", inplace=("a", "ans")),
+    # lib/PDL/Bad.pd:343-416,584-905.  $AF = F LD CF CD CLD D ("so defaults to D if non-float given", Bad.pd:6-7)
+    OpSpec("isbad", [Par("a"), Par("b", out=True, typed=T.L)], _A, "badop"),
+    OpSpec("isgood", [Par("a"), Par("b", out=True, typed=T.L)], _A, "badop"),
+    OpSpec("isnan", [Par("a"), Par("b", out=True, typed=T.L)], _A, "badop"),
+    OpSpec("setbadif", [Par("a"), Par("mask", typed=T.L), Par("b", out=True)], _A, "badop"),
+    OpSpec("setvaltobad", [Par("a"), Par("b", out=True)], _A, "badop", inplace=("a",)),
+    OpSpec("setnantobad", [Par("a"), Par("b", out=True)], _AF, "badop", inplace=("a",)),
+    OpSpec("setinftobad", [Par("a"), Par("b", out=True)], _AF, "badop", inplace=("a",)),
+    OpSpec("setnonfinitetobad", [Par("a"), Par("b", out=True)], _AF, "badop", inplace=("a",)),
+    OpSpec("setbadtonan", [Par("a"), Par("b", out=True)], _AF, "badop", inplace=("a",)),
+    OpSpec("setbadtoval", [Par("a"), Par("b", out=True)], _A, "badop", inplace=("a",)),
+    OpSpec("badmask", [Par("a"), Par("b"), Par("c", out=True)], _R, "badop", inplace=("a",)),
+    OpSpec("copybad", [Par("a"), Par("mask"), Par("b", out=True)], _A, "badop", inplace=("a",)),
+    # axisvalues, lib/PDL/Primitive.pd:1468-1474; inner, :48-70
+    OpSpec("axisvalues", [Par("i", ("n",)), Par("a", ("n",), out=True)], _A, "axis", inplace=("i",)),
+    OpSpec("inner", [Par("a", ("n",)), Par("b", ("n",)), Par("c", out=True)], _A, "inner"),
     # matmult, lib/PDL/Primitive.pd:191-195
     OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
 ]}
@@ -238,8 +260,11 @@ class Prepared:
         return self.outputs
 
 
-def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> None:
-    pdls[0].engine.readdata(_build_trans(spec, transtype, pdls, bc, named, bval))
+def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> int:
+    """One readdata.  Returns the op's `flag` (ops with a data-dependent output badflag), else 0."""
+    tr = _build_trans(spec, transtype, pdls, bc, named, bval)
+    pdls[0].engine.readdata(tr)
+    return int(tr._anybad.value) if spec.name in _STATE_IFFLAG else 0
 
 
 def _build_trans(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> _abi.Trans:
@@ -256,6 +281,11 @@ def _build_trans(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named:
         tr.ind[k] = v
     for k, v in enumerate(named.get("rinc", ())):
         tr.rinc[k] = v
+    tr.param = float(named.get("param", 0.0))
+    if spec.name in _STATE_IFFLAG:
+        import ctypes as _C
+        tr._anybad = _C.c_int32(0)      # kept alive by the descriptor that points at it
+        tr.anybad = _C.pointer(tr._anybad)
     for j, p in enumerate(pdls):
         par = tr.pdls[j]
         par.data = p.store.ptr if p.store is not None else None
@@ -277,7 +307,7 @@ def prepare_op(name: str, inputs: list, outputs: list | None = None) -> Prepared
     return run_op(name, inputs, outputs, _prepare=True)
 
 
-def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False):
+def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False, param: float = 0.0):
     """pdl_run_<name>(inputs..., outputs...).  `outputs` entries may be None (null ndarray:
     created with the broadcast dims).  Returns the output ndarrays."""
     spec = SPECS[name]
@@ -356,6 +386,14 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
             o.badflag = True
 
     named = {}
+    if spec.kind == "badop":
+        named = {"param": param}
+    elif spec.kind == "axis":
+        i, a = placeholder
+        named = {"ind": [ind["n"]], "rinc": [_real_inc(i, 0), _real_inc(a, 0)]}
+    elif spec.kind == "inner":
+        a, b, _c = placeholder
+        named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0)]}
     if spec.kind == "reduce":
         a = placeholder[0]
         named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0)]}
@@ -376,7 +414,13 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
         if temps:
             raise PDLError(f"PDL::{name}: prepare_op needs outputs already in the operation's type")
         return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder)
-    _launch(spec, transtype, placeholder, bc, named, bval)
+    flag = _launch(spec, transtype, placeholder, bc, named, bval)
+    if name in _STATE_SETBAD or (name in _STATE_IFFLAG and flag):
+        for o in placeholder[len(ins):]:
+            o.badflag = True
+    elif name in _STATE_SETGOOD:
+        for o in placeholder[len(ins):]:
+            o.badflag = False
 
     for target, o in temps:
         conv = convert_type(target, o.datatype)

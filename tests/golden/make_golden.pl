@@ -114,6 +114,17 @@ sub add_case {
       $out = PDL::ipow($args[0], $args[1]);
     } elsif ($kind eq 'convert') {
       $out = $args[0]->convert($TOBJ{$call->{to}});
+    } elsif ($kind eq 'badop') {      # PDL::Bad functions: ndarray and scalar arguments in call order
+      my $f = PDL->can($call->{op}) or die "no op $call->{op}";
+      if ($call->{inplace}) { my $a = $args[0]->copy; $a->inplace; $f->($a, @args[1..$#args]); $out = $a; }
+      else { $out = $f->(@args); }
+    } elsif ($kind eq 'axis') {       # xvals / yvals / zvals of an existing ndarray
+      my $m = $call->{op};
+      $out = $args[0]->$m;
+    } elsif ($kind eq 'sequence') {
+      $out = defined $call->{type} ? sequence($TOBJ{$call->{type}}, @{$call->{dims}}) : sequence(@{$call->{dims}});
+    } elsif ($kind eq 'inner') {
+      $out = PDL::inner($args[0], $args[1]);
     } else { die "kind $kind" }
     1;
   };
@@ -341,3 +352,77 @@ flush_cases('reduce.json');
   add_case("matmult-transposed-view", [[mk('double',[6,8],'small'), [['xchg',0,1]]],[mk('double',[8,5],'small'), [['xchg',0,1]]]], {kind=>'matmult'});
 }
 flush_cases('matmult.json');
+
+# ---------------------------------------------------------------- Bad.pd elementwise ops (Bad.pd:343-416,584-905)
+for my $t (@TYPES) {
+  my $a = with_bad(mk($t,[12],'small'), 1, 5, 11);
+  my $g = mk($t,[12],'small');
+  for my $op (qw(isbad isgood isnan)) {
+    add_case("$op-$t-bad", [[$a]], {kind=>'badop', op=>$op});
+    add_case("$op-$t-good", [[$g]], {kind=>'badop', op=>$op});
+  }
+  my $mask = pdl(long, [0,1,0,0,-3,0,0,0,2,0,0,0]);
+  add_case("setbadif-$t", [[$g],[$mask]], {kind=>'badop', op=>'setbadif'});
+  add_case("setbadif-$t-badin", [[$a],[with_bad($mask, 3)]], {kind=>'badop', op=>'setbadif'});
+  add_case("setbadif-$t-2d-rowmask", [[mk($t,[5,3],'small')],[pdl(long,[1,0,0,1,0])]], {kind=>'badop', op=>'setbadif'});
+  add_case("setbadif-$t-doublemask", [[$g],[pdl(double,[0,0.5,1,0,2.5,0,0,0,0,-1,0,0])]], {kind=>'badop', op=>'setbadif'});
+  add_case("setvaltobad-$t", [[$g],{scalar=>3, is_int=>1}], {kind=>'badop', op=>'setvaltobad'});
+  add_case("setvaltobad-$t-inplace", [[$a],{scalar=>2, is_int=>1}], {kind=>'badop', op=>'setvaltobad', inplace=>1});
+  add_case("setbadtoval-$t", [[$a],{scalar=>7, is_int=>1}], {kind=>'badop', op=>'setbadtoval'});
+  add_case("setbadtoval-$t-good", [[$g],{scalar=>7, is_int=>1}], {kind=>'badop', op=>'setbadtoval'});
+  add_case("setbadtoval-$t-inplace", [[$a],{scalar=>1, is_int=>1}], {kind=>'badop', op=>'setbadtoval', inplace=>1});
+  add_case("badmask-$t", [[$a],[mk($t,[12],'pos')]], {kind=>'badop', op=>'badmask'});
+  add_case("badmask-$t-scalar", [[$a],{scalar=>4, is_int=>1}], {kind=>'badop', op=>'badmask'});
+  add_case("copybad-$t", [[$g],[$a]], {kind=>'badop', op=>'copybad'});
+  add_case("copybad-$t-good", [[$g],[mk($t,[12],'pos')]], {kind=>'badop', op=>'copybad'});
+  add_case("setbadif-then-sumover-$t-view", [[mk($t,[20,3],'small'), [['slice','1:18:3,:']]],[pdl(long,[0,1,0,0,1,0])]], {kind=>'badop', op=>'setbadif'});
+}
+for my $t (qw(float double)) {
+  my $sp = mk($t,[22],'special');
+  my $fine = mk($t,[22],'small');
+  for my $op (qw(setnantobad setinftobad setnonfinitetobad setbadtonan isnan)) {
+    add_case("$op-$t-special", [[$sp]], {kind=>'badop', op=>$op});
+    add_case("$op-$t-finite", [[$fine]], {kind=>'badop', op=>$op});
+    add_case("$op-$t-badin", [[with_bad($sp, 0, 3)]], {kind=>'badop', op=>$op});
+  }
+  add_case("setnantobad-$t-inplace", [[$sp]], {kind=>'badop', op=>'setnantobad', inplace=>1});
+  add_case("setbadtonan-$t-inplace", [[with_bad($fine, 2, 9)]], {kind=>'badop', op=>'setbadtonan', inplace=>1});
+  add_case("badmask-$t-special", [[$sp],{scalar=>-1, is_int=>1}], {kind=>'badop', op=>'badmask'});
+  add_case("setvaltobad-$t-frac", [[$fine],{scalar=>1.5}], {kind=>'badop', op=>'setvaltobad'});
+  # a value equal to the default badvalue in an ndarray WITHOUT the badflag: setbadtonan still tests it (Bad.pd:795)
+  my $raw = $t eq 'float' ? pdl(float, [1, -3.4028234663852886e38, 3]) : pdl(double, [1, -1.7976931348623157e308, 3]);
+  add_case("setbadtonan-$t-noflag-badvalue", [[$raw]], {kind=>'badop', op=>'setbadtonan'});
+  add_case("setbadtoval-$t-noflag-badvalue", [[$raw],{scalar=>0, is_int=>1}], {kind=>'badop', op=>'setbadtoval'});
+  my $d = mk($t,[22],'special')->copy; $d->badflag(1); $d->badvalue($NAN);
+  add_case("isbad-$t-nan-badvalue", [[$d]], {kind=>'badop', op=>'isbad'});
+  add_case("setbadtoval-$t-nan-badvalue", [[$d],{scalar=>9, is_int=>1}], {kind=>'badop', op=>'setbadtoval'});
+}
+add_case("setnantobad-long", [[mk('long',[6],'small')]], {kind=>'badop', op=>'setnantobad'});
+add_case("setvaltobad-byte-300", [[mk('byte',[9],'mixed')],{scalar=>300, is_int=>1}], {kind=>'badop', op=>'setvaltobad'});
+flush_cases('badops.json');
+
+# ---------------------------------------------------------------- constructors (Basic.pm:117-129,479-485; Primitive.pd:1468-1474)
+for my $t (@TYPES) {
+  add_case("sequence-$t", [], {kind=>'sequence', type=>$t, dims=>[7,3]});
+  add_case("sequence-$t-long", [], {kind=>'sequence', type=>$t, dims=>[300]});
+  for my $op (qw(xvals yvals zvals)) {
+    add_case("$op-$t", [[mk($t,[5,3,2],'small')]], {kind=>'axis', op=>$op});
+  }
+  add_case("yvals-$t-1d", [[mk($t,[5],'small')]], {kind=>'axis', op=>'yvals'});
+}
+add_case("sequence-untyped", [], {kind=>'sequence', dims=>[4,2]});
+add_case("sequence-empty", [], {kind=>'sequence', type=>'long', dims=>[0,3]});
+add_case("xvals-of-view", [[mk('double',[10,4],'small'), [['slice','1:8:2,:'],['xchg',0,1]]]], {kind=>'axis', op=>'xvals'});
+flush_cases('basic.json');
+
+# ---------------------------------------------------------------- inner (Primitive.pd:48-70)
+for my $t (@TYPES) {
+  add_case("inner-$t", [[mk($t,[13,4],'small')],[mk($t,[13,4],'small')]], {kind=>'inner'}, $IS_INT{$t} ? undef : 0);
+  add_case("inner-$t-broadcast", [[mk($t,[9,3],'small')],[mk($t,[9],'small')]], {kind=>'inner'}, $IS_INT{$t} ? undef : 0);
+  add_case("inner-$t-long-row", [[mk($t,[3000],'small')],[mk($t,[3000],'small')]], {kind=>'inner'}, $IS_INT{$t} ? undef : 0) unless $BITS{$t} && $BITS{$t} < 32;
+  add_case("inner-$t-bad", [[with_bad(mk($t,[9,4],'small'), 3, 20)],[with_bad(mk($t,[9,4],'small'), 30)]], {kind=>'inner'}, $IS_INT{$t} ? undef : 0);
+  add_case("inner-$t-outer-views", [[mk($t,[8],'small'), [['dummy',1,1]]],[mk($t,[6],'small'), [['dummy',0,1]]]], {kind=>'inner'}, $IS_INT{$t} ? undef : 0);
+  add_case("inner-$t-empty-n", [[mk($t,[0,3],'small')],[mk($t,[0,3],'small')]], {kind=>'inner'});
+}
+add_case("inner-mismatch", [[mk('double',[3],'small')],[mk('double',[4],'small')]], {kind=>'inner'});
+flush_cases('inner.json');

@@ -8,7 +8,7 @@ from pathlib import Path
 import numpy as np
 
 import pdl_b200 as P
-from pdl_b200 import types as T, ufunc, ops
+from pdl_b200 import types as T, ufunc, ops, bad, basic
 from pdl_b200.engine import PDLError
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
@@ -56,6 +56,20 @@ def run_call(call, args):
         return ops.ipow(args[0], args[1])
     if kind == "convert":
         return args[0].convert(TYPE_ID[call["to"]])
+    if kind == "badop":
+        f = getattr(bad, call["op"])
+        if call.get("inplace"):
+            a = args[0].copy()
+            a.badflag = args[0].badflag
+            f(a.inplace(), *args[1:])
+            return a
+        return f(*args)
+    if kind == "axis":
+        return getattr(basic, call["op"])(args[0])
+    if kind == "sequence":
+        return basic.sequence(TYPE_ID[call["type"]] if call.get("type") else None, *call["dims"], engine=call["_engine"])
+    if kind == "inner":
+        return P.inner(args[0], args[1])
     raise ValueError(kind)
 
 
@@ -81,12 +95,14 @@ def ulp_diff(got: np.ndarray, want: np.ndarray) -> int:
 def check_case(case, engine):
     """Replay one recorded case on `engine`; assert type, dims, badflag and values."""
     args = [build_input(s, engine) for s in case["inputs"]]
+    case["call"]["_engine"] = engine
     if "error" in case:
         try:
             run_call(case["call"], args)
         except PDLError as e:
             want = case["error"]
-            key = "Mismatched implicit broadcast dimension" if "Mismatched" in want else "Dim mismatch in matmult"
+            key = ("Mismatched implicit broadcast dimension" if "Mismatched" in want else
+                   "index 'n' size 3, but ndarray dim has size 4" if "index 'n'" in want else "Dim mismatch in matmult")
             assert key in str(e), (str(e), want)
             if "Dim mismatch" in want:
                 assert str(e).strip() == want.strip()

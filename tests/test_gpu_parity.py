@@ -284,3 +284,120 @@ def test_ipow(engines, t):
     (ga, oa), (ge, oe) = both(engines, a, t), both(engines, e, T.LL)
     assert_same(f"ipow-{T.NAMES[t]}", ops.ipow(ga, ge), ops.ipow(oa, oe))       # same multiplication chain: bit-exact
     assert_same(f"ipow-{T.NAMES[t]}-scalar", ops.ipow(ga, 3), ops.ipow(oa, 3))
+
+
+# ---- Bad.pd elementwise ops, axisvalues, inner ------------------------------
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_bad_producers_consumers(engines, t):
+    from pdl_b200 import bad as B
+    rng = np.random.default_rng(900 + t)
+    shape = (257, 1031)   # PDL dims [1031, 257]: tile bodies, tails and row decode
+    a = rand_array(rng, t, shape, "small")
+    badv = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+    ab = a.copy(); ab[rng.random(shape) < 0.03] = badv
+    mask = (rng.random(shape) < 0.2).astype(np.int32) * rng.integers(-3, 3, size=shape, endpoint=True).astype(np.int32)
+    rowmask = (rng.random(shape[1]) < 0.5).astype(np.int32)
+    other = rand_array(rng, t, shape, "pos")
+    for flagged, arr in ((False, a), (True, ab)):
+        tag = f"{T.NAMES[t]}-{'bad' if flagged else 'good'}"
+        (ga, oa) = both(engines, arr, t, flagged)
+        for op in ("isbad", "isgood", "isnan"):
+            assert_same(f"{op}-{tag}", getattr(B, op)(ga), getattr(B, op)(oa))
+        (gm, om) = both(engines, mask, T.L)
+        assert_same(f"setbadif-{tag}", B.setbadif(ga, gm), B.setbadif(oa, om))
+        (gr, orr) = both(engines, rowmask, T.L)
+        assert_same(f"setbadif-row-{tag}", B.setbadif(ga, gr), B.setbadif(oa, orr))
+        assert_same(f"setvaltobad-{tag}", B.setvaltobad(ga, 3), B.setvaltobad(oa, 3))
+        assert_same(f"setbadtoval-{tag}", B.setbadtoval(ga, 5), B.setbadtoval(oa, 5))
+        (gb, ob) = both(engines, other, t)
+        assert_same(f"badmask-{tag}", B.badmask(ga, gb), B.badmask(oa, ob))
+        (gc, oc) = both(engines, ab, t, True)
+        assert_same(f"copybad-{tag}", B.copybad(gb, gc), B.copybad(ob, oc))
+        # strided / transposed views are read in place
+        assert_same(f"setbadtoval-view-{tag}", B.setbadtoval(ga.slice("1:-1:3,:").xchg(0, 1), 1),
+                    B.setbadtoval(oa.slice("1:-1:3,:").xchg(0, 1), 1))
+        # in place
+        gi, oi = ga.copy(), oa.copy()
+        gi.badflag = oi.badflag = flagged
+        B.setbadtoval(gi.inplace(), 2); B.setbadtoval(oi.inplace(), 2)
+        assert_same(f"setbadtoval-inplace-{tag}", gi, oi)
+
+
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_nonfinite_to_bad(engines, t):
+    from pdl_b200 import bad as B
+    rng = np.random.default_rng(950 + t)
+    n = 300_001
+    a = rand_array(rng, t, (n,))
+    k = rng.integers(0, n, size=900)
+    special = a.copy()
+    special[k[:300]] = np.nan; special[k[300:600]] = np.inf; special[k[600:]] = -np.inf
+    only_inf = a.copy(); only_inf[k[:10]] = np.inf
+    for name, arr in (("finite", a), ("special", special), ("inf", only_inf)):
+        for flagged in (False, True):
+            (ga, oa) = both(engines, arr, t, flagged)
+            for op in ("setnantobad", "setinftobad", "setnonfinitetobad", "setbadtonan", "isnan"):
+                assert_same(f"{op}-{name}-{T.NAMES[t]}-{flagged}", getattr(B, op)(ga), getattr(B, op)(oa))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_axisvalues_constructors(engines, t):
+    from pdl_b200 import basic
+    for e_out in ([basic.sequence(t, 1000, 37, engine=e) for e in engines],
+                  [basic.sequence(t, 100_003, engine=e) for e in engines],
+                  [basic.zeroes(t, 513, 7, engine=e) for e in engines],
+                  [basic.ones(t, 513, 7, engine=e) for e in engines]):
+        assert_same(f"ctor-{T.NAMES[t]}", e_out[0], e_out[1])
+    rng = np.random.default_rng(980 + t)
+    a = rand_array(rng, t, (5, 33, 129), "small")
+    (ga, oa) = both(engines, a, t)
+    for f in (basic.xvals, basic.yvals, basic.zvals):
+        assert_same(f"{f.__name__}-{T.NAMES[t]}", f(ga), f(oa))
+        assert_same(f"{f.__name__}-view-{T.NAMES[t]}", f(ga.slice("1:-1:2,:,:").xchg(0, 2)), f(oa.slice("1:-1:2,:,:").xchg(0, 2)))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_inner(engines, t):
+    rng = np.random.default_rng(990 + t)
+    # exact-by-construction values: every product and partial sum is representable, so the 80-bit
+    # sequential sum of the reference and the device's chunked sums must agree bit for bit
+    flav = "exact" if t in (T.F, T.D) else "small"
+    for shape in ((3, 70_001), (2000, 33), (7, 300), (1, 5)):
+        a, b = rand_array(rng, t, shape, flav), rand_array(rng, t, shape, flav)
+        if T.SIZE[t] == 1:
+            a, b = a % 2, b % 2          # keep the row sums inside the 8-bit output type
+        elif T.SIZE[t] == 2 and shape[1] > 1000:
+            a, b = a % 2, b % 2
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"inner-{T.NAMES[t]}-{shape}", P.inner(ga, gb), P.inner(oa, ob))
+        # b broadcast along the rows, and BAD rows
+        (gv, ov) = both(engines, b[0], t)
+        assert_same(f"inner-bcast-{T.NAMES[t]}-{shape}", P.inner(ga, gv), P.inner(oa, ov))
+        ab = a.copy(); ab[rng.random(shape) < 0.001] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        (gx, ox) = both(engines, ab, t, True)
+        assert_same(f"inner-bad-{T.NAMES[t]}-{shape}", P.inner(gx, gb), P.inner(ox, ob))
+    # the cfg3 shape: [N,1] x [1,M] dummies, fused mult -> sumover
+    x, y = rand_array(rng, t, (300,), flav), rand_array(rng, t, (200,), flav)
+    if T.SIZE[t] <= 2:
+        x, y = x % 2, y % 2
+    (gx, ox), (gy, oy) = both(engines, x, t), both(engines, y, t)
+    fused = [P.inner(px.dummy(1, 1), py.dummy(0, 1)) for px, py in ((gx, gy), (ox, oy))]
+    assert_same(f"inner-outer-{T.NAMES[t]}", fused[0], fused[1])
+    if t in (T.L, T.LL, T.F, T.D):   # same result type as sumover there (no int+ widening)
+        unfused = ufunc.sumover(gx.dummy(1, 1) * gy.dummy(0, 1))
+        assert fused[0].to_numpy().tobytes() == unfused.to_numpy().tobytes()
+
+
+def test_inner_double_random_within_tolerance(engines):
+    """Inexact doubles: the reference sums in x87 80-bit, the device in a compensated double pair;
+    both are within 1 ulp of the exact sum, so they differ by at most 1 ulp of the result
+    (|result| bounded away from cancellation by using positive values)."""
+    rng = np.random.default_rng(77)
+    a = rng.random((4, 100_000)) + 0.5
+    b = rng.random((4, 100_000)) + 0.5
+    (ga, oa), (gb, ob) = both(engines, a, T.D), both(engines, b, T.D)
+    assert_same("inner-double-random", P.inner(ga, gb), P.inner(oa, ob), tol_ulp=1)
+    af, bf = a.astype(np.float32), b.astype(np.float32)
+    (ga, oa), (gb, ob) = both(engines, af, T.F), both(engines, bf, T.F)
+    assert_same("inner-float-random", P.inner(ga, gb), P.inner(oa, ob), tol_ulp=1)
