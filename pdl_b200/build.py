@@ -28,6 +28,7 @@ FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    "-Xfatbin=-compress-all",   # 3x smaller .so: the in-tree library travels to the GPU box with every snapshot
 ]
 
 

@@ -29,7 +29,7 @@
 
 static Core *PDL;
 
-#define MAX_HOOKS 64
+#define MAX_HOOKS 128
 typedef struct {
   pdl_transvtable *vt;
   pdlb200_trans_fn orig_readdata, orig_redodims;

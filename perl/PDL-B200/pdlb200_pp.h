@@ -137,6 +137,7 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
   pdlb200_trans d;
   pdlb200_pp_staged_t st[PDLB200_MAXPDLS];
   int nst = 0, rc, on_device = pdlb200_pp_enabled;
+  int32_t anybad = 0;
   PDL_Indx i, j, npdls = vt->npdls;
   char err[512];
   if (tr->__datatype > PDL_D || npdls > PDLB200_MAXPDLS || tr->broadcast.ndims > PDLB200_MAXDIMS) on_device = 0;
@@ -164,6 +165,10 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
     d.ind[0] = tr->ind_sizes[0];
     for (i = 0; i < vt->nind_ids && i < 8; i++) d.rinc[i] = tr->inc_sizes[i];
   }
+  /* OtherPars: setvaltobad(double value) / setbadtoval(double newval) — the params struct holds that one double
+   * ([gen] Bad-pp-setvaltobad.c: typedef struct pdl_params_setvaltobad { double value; }) */
+  if ((opid == PDLB200_OP_SETVALTOBAD || opid == PDLB200_OP_SETBADTOVAL) && tr->params) d.param = *(double *)tr->params;
+  d.anybad = &anybad;
   pdlb200_pp_stage_used = 0;
   for (j = 0; j < npdls; j++) {
     pdl *p = tr->pdls[j];
@@ -188,6 +193,12 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
   /* outputs flagged BAD by the op itself: minimum/maximum(_ind) with no good element (Ufunc.pd:463-464) */
   if (opid >= PDLB200_OP_MINIMUM && opid <= PDLB200_OP_MAXIMUM_IND && !tr->bvalflag && tr->ind_sizes[0] == 0)
     tr->pdls[1]->state |= PDL_BADVAL;
+  /* $PDLSTATESETBAD / $PDLSTATESETGOOD of the Bad.pd bodies (Bad.pd:634,676,695-707,805,838,857) */
+  if (opid == PDLB200_OP_SETBADIF || opid == PDLB200_OP_SETVALTOBAD ||
+      (anybad && opid >= PDLB200_OP_SETNANTOBAD && opid <= PDLB200_OP_SETNONFINITETOBAD))
+    tr->pdls[npdls - 1]->state |= PDL_BADVAL;
+  else if (opid == PDLB200_OP_SETBADTONAN || opid == PDLB200_OP_SETBADTOVAL || opid == PDLB200_OP_BADMASK)
+    tr->pdls[npdls - 1]->state &= ~PDL_BADVAL;
   pdlb200_pp_device_calls++;
   if (pdlb200_pp_verbose) fprintf(stderr, "PDL::B200 %s -> %s\n", vt->name, pdlb200_last_kernel());
   return PDL_err;

@@ -59,6 +59,34 @@ for my $t (@types) {
   both("bad sumover $t", sub { $bad->sumover });
   both("bad average $t", sub { $bad->average });
   both("bad minimum $t", sub { $bad->minimum });
+  # the rows either side of the path (SURVEY.md §8(f)): Bad.pd ops, constructors, scans, inner
+  my $mask = ($a->abs % 5 == 0);
+  both("isbad $t",        sub { $bad->isbad });
+  both("isgood $t",       sub { $bad->isgood });
+  both("setbadif $t",     sub { $a->setbadif($mask) });
+  both("setbadif+sum $t", sub { $a->setbadif($mask)->sumover });
+  both("setvaltobad $t",  sub { $a->setvaltobad(7) });
+  both("setbadtoval $t",  sub { $bad->setbadtoval(3) });
+  both("setbadtoval inplace $t", sub { my $q = $bad->copy; $q->inplace->setbadtoval(1); $q });
+  both("copybad $t",      sub { $b->copybad($bad) });
+  both("badmask $t",      sub { $bad->badmask(5) });
+  both("nbadover $t",     sub { $bad->nbadover });
+  both("cumusumover $t",  sub { ($a % 7)->cumusumover });
+  both("bad cumusumover $t", sub { $bad->cumusumover });
+  both("xvals $t",        sub { $a->xvals });
+  both("yvals $t",        sub { $a->yvals });
+  both("sequence $t",     sub { sequence($t, 301, 5) });
+  both("inner $t",        sub { inner($a % 3, $b % 3) });
+  both("inner bad $t",    sub { inner($bad % 3, $b % 3) });
+  if (!$t->integer) {
+    my $sp = $a->copy; $sp->set(3, 1, 'nan'); $sp->set(4, 2, 'inf');
+    both("setnantobad $t",       sub { $sp->setnantobad });
+    both("setnantobad clean $t", sub { $a->setnantobad });
+    both("setinftobad $t",       sub { $sp->setinftobad });
+    both("setnonfinitetobad $t", sub { $sp->setnonfinitetobad });
+    both("setbadtonan $t",       sub { $bad->setbadtonan });
+    both("isnan $t",             sub { $sp->isnan });
+  }
 }
 # large: exercises the managed-memory path (outputs created managed, inputs migrated on first use)
 {

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-config kernel timings (CUDA events, inputs resident, L2-cold by rotation or size) for
 the BASELINE.json configs other than the bench.py headline.  Prints one JSON line per config.
-Usage: python tools/microbench.py [cfg1] [cfg3] [cfg4] [cfg5] [--reps N]"""
+`next` times the SURVEY.md §8(f) rows (Bad.pd ops, constructors, inner, scans).
+Usage: python tools/microbench.py [cfg1] [cfg3] [cfg4] [cfg5] [next] [--reps N]"""
 from __future__ import annotations
 
 import json
@@ -45,7 +46,7 @@ def main():
     reps = 20
     if "--reps" in sys.argv:
         reps = int(sys.argv[sys.argv.index("--reps") + 1])
-    want = set(args) or {"cfg1", "cfg3", "cfg4", "cfg5"}
+    want = set(args) or {"cfg1", "cfg3", "cfg4", "cfg5", "next"}
     eng = P.CudaEngine(0)
     P.set_default_engine(eng)
     dev = torch.device("cuda", 0)
@@ -151,6 +152,49 @@ def main():
                           "frac": by / ms_s / 1e6 / PEAK, "sum": o1.sclr(), "exact": o1.sclr() == ref}))
         print(json.dumps({"cfg": f"cfg5 max of float[2^{int(np.log2(n))}] on 1 GPU", "ms": ms_m, "gbs": by / ms_m / 1e6,
                           "frac": by / ms_m / 1e6 / PEAK, "max": o2.sclr()}))
+
+    if "next" in want:
+        from pdl_b200 import bad as B, basic
+        n = 2 ** 28          # 1 GiB of float per operand: far beyond L2
+        x = torch.randint(-8, 9, (n,), device=dev, generator=g).float()
+        x[torch.rand(n, device=dev, generator=g) < 0.01] = -3.4028234663852886e38
+        m = (torch.rand(n, device=dev, generator=g) < 0.1).int()
+        px, pm = wrap(eng, x, T.F, [n]), wrap(eng, m, T.L, [n])
+        px.badflag = True
+        of, ol = P.PDL.empty(T.F, [n], eng), P.PDL.empty(T.L, [n], eng)
+
+        def row(name, fn, by, r=reps, **extra):
+            ms = timeit(fn, r)
+            print(json.dumps({"cfg": name, "ms": ms, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / PEAK,
+                              "kernel": eng.last_kernel(), **extra}))
+        row("next setbadif float[2^28] + int mask", lambda: P.run_op("setbadif", [px, pm], [of]), 12 * n)
+        row("next setbadtoval float[2^28], 1% BAD", lambda: P.run_op("setbadtoval", [px], [of], param=0.0), 8 * n)
+        row("next isbad float[2^28] -> long", lambda: P.run_op("isbad", [px], [ol]), 8 * n)
+        row("next copybad float[2^28]", lambda: P.run_op("copybad", [of, px], [of]), 12 * n)
+        row("next sequence(float, 2^28) (axisvalues, write only)", lambda: P.run_op("axisvalues", [of], [of]), 4 * n)
+        od = P.PDL.empty(T.D, [n // 2], eng)
+        row("next sequence(double, 2^27)", lambda: P.run_op("axisvalues", [od], [od]), 8 * (n // 2))
+        py_ = wrap(eng, torch.randint(-8, 9, (n,), device=dev, generator=g).float(), T.F, [n])
+        px.badflag = False
+        o0 = P.PDL.empty(T.F, [], eng)
+        row("next inner of two float[2^28] (dot product)", lambda: P.run_op("inner", [px, py_], [o0]), 8 * n)
+        row("next cumusumover float[2^28] (one row, 3-pass chunked scan)", lambda: P.run_op("cumusumover", [py_], [of]), 8 * n)
+        x2 = wrap(eng, x, T.F, [16384, n // 16384])
+        o2 = wrap(eng, torch.empty(n, dtype=torch.float32, device=dev), T.F, [16384, n // 16384])
+        row("next cumusumover float[16384,16384] (warp per row)", lambda: P.run_op("cumusumover", [x2], [o2]), 8 * n)
+        del x, m, px, pm, of, ol, od, py_, x2, o2
+        # cfg3 fused: inner([N,1] strided, [1,M] strided) == sumover(mult(...)) without the 8 GiB intermediate
+        N = M = 32768
+        big1 = torch.randint(-1024, 1024, (2 * N,), device=dev, generator=g).double() / 256
+        big2 = torch.randint(-1024, 1024, (2 * M,), device=dev, generator=g).double() / 256
+        a = wrap(eng, big1, T.D, [2 * N]).slice("0:-1:2").dummy(1, 1)
+        b = wrap(eng, big2, T.D, [2 * M]).slice("0:-1:2").dummy(0, 1)
+        out = P.PDL.empty(T.D, [M], eng)
+        ms = timeit(lambda: P.run_op("inner", [a, b], [out]), reps)
+        ref = (big1[::2].sum() * big2[::2]).cpu().numpy()
+        print(json.dumps({"cfg": "next cfg3 FUSED: inner([N,1],[1,M]) N=M=32768 double (reported apart from the roofline figure)",
+                          "ms": ms, "madds_per_sec": N * M / ms * 1e3, "traffic_bytes": 8 * (N + 2 * M),
+                          "bitexact_vs_closed_form": bool(np.array_equal(out.to_numpy(), ref))}))
 
 
 if __name__ == "__main__":
