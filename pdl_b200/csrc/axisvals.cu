@@ -22,9 +22,16 @@ template <class T>
 __global__ void __launch_bounds__(256) axisvals_kernel(const __grid_constant__ AxPlan p) {
   constexpr int VEC = 16 / sizeof(T);
   T *base = reinterpret_cast<T *>(p.a);
-  for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < p.n_units; u += (int64_t)gridDim.x * blockDim.x) {
+  constexpr int U = 4;   // independent 128-bit stores per thread per trip
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t u0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u0 < p.n_units; u0 += nthreads * U) {
+#pragma unroll
+   for (int j = 0; j < U; j++) {
+    const int64_t u = u0 + j * nthreads;
+    if (u >= p.n_units) break;
     int64_t row, v;
-    if ((uint64_t)p.n_units <= 0xffffffffull) { const uint32_t r = (uint32_t)u / (uint32_t)p.vpr; row = r; v = (uint32_t)u - r * (uint32_t)p.vpr; }
+    if (p.nd == 1) { row = 0; v = u; }
+    else if ((uint64_t)p.n_units <= 0xffffffffull) { const uint32_t r = (uint32_t)u / (uint32_t)p.vpr; row = r; v = (uint32_t)u - r * (uint32_t)p.vpr; }
     else { row = u / p.vpr; v = u - row * p.vpr; }
     const int64_t i0 = v * VEC;
     int64_t off = i0 * p.st[0];
@@ -35,21 +42,33 @@ __global__ void __launch_bounds__(256) axisvals_kernel(const __grid_constant__ A
     }
     const int64_t left = p.dims[0] - i0;
     const int cnt = left < VEC ? (int)left : VEC;
-    int64_t m = ((uint64_t)i0 <= 0xffffffffull && (uint64_t)p.n <= 0xffffffffull) ? (int64_t)((uint32_t)i0 % (uint32_t)p.n) : i0 % p.n;
+    int64_t m = (p.n == p.dims[0]) ? i0     // nothing was merged into dim 0: the position IS n
+              : ((uint64_t)i0 <= 0xffffffffull && (uint64_t)p.n <= 0xffffffffull) ? (int64_t)((uint32_t)i0 % (uint32_t)p.n) : i0 % p.n;
     Pack<T> r;
+    // floating point: while the values are exactly representable consecutive integers, one conversion and
+    // VEC-1 exact additions replace VEC (quarter-rate) int->float conversions
+    constexpr int64_t EXACT = tt<T>::is_int ? 0 : (sizeof(T) == 4 ? (1ll << 24) : (1ll << 53));
+    if (!tt<T>::is_int && m + VEC <= p.n && m + VEC <= EXACT) {
+      const T b0 = (m <= 0x7fffffff) ? (T)(int)m : (T)m;
 #pragma unroll
-    for (int k = 0; k < VEC; k++) { r.e[k] = (T)m; if (++m == p.n) m = 0; }
+      for (int k = 0; k < VEC; k++) r.e[k] = b0 + (T)k;
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; k++) { r.e[k] = (T)m; if (++m == p.n) m = 0; }
+    }
     if (p.vec && cnt == VEC) *reinterpret_cast<uint4 *>(base + off) = r.q;
     else {
 #pragma unroll
       for (int k = 0; k < VEC; k++) if (k < cnt) base[off + k * p.st[0]] = r.e[k];
     }
+   }
   }
 }
 
 template <class T>
 static int ax_go(const AxPlan &p, cudaStream_t s, const Err &E) {
-  int64_t g = (p.n_units + 255) / 256;
+  int64_t g = (p.n_units + 256 * 4 - 1) / (256 * 4);
+  if (g < 1) g = 1;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (g > cap) g = cap;
   axisvals_kernel<T><<<(int)g, 256, 0, s>>>(p);

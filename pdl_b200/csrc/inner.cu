@@ -116,10 +116,39 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
     InAcc<T> acc; acc.init();
     constexpr int U = 4;
     int64_t n = lo + lane;
+    // unit-stride, 16-byte aligned chunk: 128-bit loads, U per operand in flight per lane
+    constexpr int VEC = 16 / sizeof(T);
+    if (p.inc_a == 1 && p.inc_b == 1 && ((((uintptr_t)(pa + lo)) | ((uintptr_t)(pb + lo))) & 15) == 0) {
+      const int64_t nvec = (hi - lo) / VEC;
+      const uint4 *qa = reinterpret_cast<const uint4 *>(pa + lo), *qb = reinterpret_cast<const uint4 *>(pb + lo);
+      for (int64_t v0 = 0; v0 < nvec; v0 += 32 * U) {
+        Pack<T> ra[U], rb[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int64_t j = v0 + u * 32 + lane; if (j < nvec) { ra[u].q = qa[j]; rb[u].q = qb[j]; } }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (v0 + u * 32 + lane < nvec) {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+              const T va = ra[u].e[k], vb = rb[u].e[k];
+              if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
+              else acc.add(va, vb);
+            }
+          }
+        }
+      }
+      n = lo + nvec * VEC + lane;     // tail elements go through the scalar loop below
+    }
+    // an operand that does not move along n (dummy dim: the cfg3 outer-product shape) is read once per row
+    const bool a_const = p.inc_a == 0, b_const = p.inc_b == 0;
+    const T a0 = (a_const && p.n > 0) ? pa[0] : T(0), b0 = (b_const && p.n > 0) ? pb[0] : T(0);
     for (; n + (U - 1) * 32 < hi; n += U * 32) {
       T va[U], vb[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) { va[u] = pa[(n + u * 32) * p.inc_a]; vb[u] = pb[(n + u * 32) * p.inc_b]; }
+      for (int u = 0; u < U; u++) {
+        va[u] = a_const ? a0 : pa[(n + u * 32) * p.inc_a];
+        vb[u] = b_const ? b0 : pb[(n + u * 32) * p.inc_b];
+      }
 #pragma unroll
       for (int u = 0; u < U; u++) {
         if (p.badmode && (is_bad(va[u], abad, p.abadnan != 0) || is_bad(vb[u], bbad, p.bbadnan != 0))) acc.bad = 1;
@@ -127,7 +156,7 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
       }
     }
     for (; n < hi; n += 32) {
-      const T va = pa[n * p.inc_a], vb = pb[n * p.inc_b];
+      const T va = a_const ? a0 : pa[n * p.inc_a], vb = b_const ? b0 : pb[n * p.inc_b];
       if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
       else acc.add(va, vb);
     }
@@ -140,16 +169,19 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
   }
 }
 
-// finishing pass: one thread per row merges the chunk partials in chunk order
+// finishing pass: one warp per row merges the chunk partials (lanes stride over the chunks, then a shuffle tree)
 template <class T>
 __global__ void __launch_bounds__(256) inner_finish_kernel(const __grid_constant__ InPlan p) {
-  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.nrows; row += (int64_t)gridDim.x * 8) {
     int64_t oa, ob, oc;
     in_row_offsets<T>(p, row, oa, ob, oc);
     const InAcc<T> *part = reinterpret_cast<const InAcc<T> *>(p.part) + row * p.nchunks;
-    InAcc<T> acc = part[0];
-    for (int64_t k = 1; k < p.nchunks; k++) acc.merge(part[k]);
-    in_write<T>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+    InAcc<T> acc; acc.init();
+    for (int64_t k = lane; k < p.nchunks; k += 32) acc.merge(part[k]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { const InAcc<T> o = shfl_down_acc(acc, d); acc.merge(o); }
+    if (lane == 0) in_write<T>(p, reinterpret_cast<T *>(p.c) + oc, acc);
   }
 }
 
@@ -196,7 +228,7 @@ static int inner_go(InPlan &p, cudaStream_t s, const Err &E) {
     if (g > cap * 4) g = cap * 4;
     inner_warp_kernel<T><<<(int)g, 256, 0, s>>>(p);
     if (p.nchunks > 1) {
-      int64_t g2 = (p.nrows + 255) / 256;
+      int64_t g2 = (p.nrows + 7) / 8;
       if (g2 > cap) g2 = cap;
       inner_finish_kernel<T><<<(int)g2, 256, 0, s>>>(p);
       note_launch("inner");

@@ -1,14 +1,17 @@
 // scan.cu — cumusumover / cumuprodover (+d variants), lib/PDL/Ufunc.pd:120-141: a(n); [o]b(n).
-// Two kernels:
+// Kernels:
 //  * scan_rows_kernel: one thread per row walks n sequentially — the reference's own order, so float
 //    results are bit-exact; coalesced when a broadcast dim is the unit-stride one (many short rows).
-//  * scan_warp_kernel: one warp per row for long rows: 32 consecutive elements per step (coalesced),
-//    Kogge-Stone scan by shuffles, carry to the next step.  Integer results are bit-exact (wrap-around
-//    add/multiply is associative); float results differ from the sequential order only in rounding.
-//  * few very long rows (a 1-D cumusumover is the common case): three passes over chunks of
-//    a multiple of SC_CHUNK elements (sized for one resident wave of warps), one warp per (row, chunk): (1) chunk totals, (2) exclusive scan of the totals
-//    per row, (3) the warp scan again with the chunk's carry-in.  3 passes of traffic instead of the
-//    ideal 2, but every SM works on the row.
+//  * scan_chunk_kernel<APPLY>: one warp per (row, chunk).  Unit-stride 16-byte-aligned chunks move as
+//    128-bit vectors, 4 in flight per lane: each lane scans its vector, the lane totals are scanned
+//    across the warp by shuffles (Kogge-Stone), the carry moves on to the next step; other layouts
+//    take 32 consecutive elements per step.  Integer results are bit-exact (wrap-around add/multiply
+//    is associative); float results differ from the sequential order only in rounding.
+//    - long rows, many of them: one chunk = the whole row, no carry-in.
+//    - few very long rows (a 1-D cumusumover is the common case): three passes over chunks of a
+//      multiple of SC_CHUNK elements sized for one resident wave of warps: (1) chunk totals,
+//      (2) scan_chunk_prefix_kernel: exclusive scan of the totals per row, (3) the scan again with
+//      the chunk's carry-in.  3 passes of traffic instead of the ideal 2, but every SM works on the row.
 #include <cstring>
 #include "common.cuh"
 namespace pdlb200 {
@@ -93,42 +96,6 @@ template <class O> __device__ __forceinline__ O shfl_idx_t(O v, int src) {
   }
 }
 
-template <class T, class O, bool PROD>
-__global__ void __launch_bounds__(256) scan_warp_kernel(const __grid_constant__ ScPlan p) {
-  const T abad = from_bits<T>(p.abad);
-  const O bbad = from_bits<O>(p.bbad);
-  const O ident = PROD ? O(1) : O(0);
-  const int lane = threadIdx.x & 31;
-  int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t row_step = (int64_t)gridDim.x * 8;
-  for (; row < p.nrows; row += row_step) {
-    int64_t oa = 0, ob = 0, r = row;
-    for (int d = 0; d < p.nd; d++) {
-      const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d];
-      const int64_t i = r - q * p.dims[d];
-      oa += i * p.sa[d]; ob += i * p.sb[d]; r = q;
-    }
-    const T *pa = reinterpret_cast<const T *>(p.a) + oa;
-    O *pb = reinterpret_cast<O *>(p.b) + ob;
-    O carry = ident;
-    for (int64_t n0 = 0; n0 < p.n; n0 += 32) {
-      const int64_t n = n0 + lane;
-      const bool in = n < p.n;
-      const T v = in ? pa[n * p.inc_a] : T(0);
-      const bool bad = in && p.badmode && is_bad(v, abad, p.abadnan != 0);
-      O x = (in && !bad) ? (O)v : ident;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const O y = shfl_up_t(x, d);
-        if (lane >= d) x = scan_op<O, PROD>(y, x);
-      }
-      const O res = scan_op<O, PROD>(carry, x);
-      if (in) pb[n * p.inc_b] = bad ? bbad : res;
-      carry = shfl_idx_t(res, 31);
-    }
-  }
-}
-
 // chunked mode, pass 1 and 3.  APPLY=false: write the chunk's total (good elements only) to carry[row][chunk];
 // APPLY=true: scan the chunk starting from carry[row][chunk] (already turned into an exclusive prefix by pass 2).
 template <class T, class O, bool PROD, bool APPLY>
@@ -149,9 +116,9 @@ __global__ void __launch_bounds__(256) scan_chunk_kernel(const __grid_constant__
     }
     const T *pa = reinterpret_cast<const T *>(p.a) + oa;
     O *pb = reinterpret_cast<O *>(p.b) + ob;
-    O *cw = reinterpret_cast<O *>(p.carry) + w;
+    O *cw = reinterpret_cast<O *>(p.carry) + w;     // not dereferenced when p.carry is NULL (whole rows, no carry-in)
     const int64_t lo = chunk * p.chunk, hi = (lo + p.chunk < p.n) ? lo + p.chunk : p.n;
-    O carry = APPLY ? *cw : ident;
+    O carry = (APPLY && p.carry) ? *cw : ident;
     constexpr int VEC = 16 / sizeof(T);
     // vector path: same-size in/out, unit strides, 16-byte aligned chunk starts (p.chunk is a multiple of SC_CHUNK, hence of every VEC)
     const bool vec = sizeof(T) == sizeof(O) && p.inc_a == 1 && (!APPLY || p.inc_b == 1) &&
@@ -306,9 +273,13 @@ static int scan_go(const ScPlan &p, cudaStream_t s, const char *name, const Err 
     scan_chunk_kernel<T, O, PROD, true><<<(int)g, 256, 0, s>>>(q);
     note_launch(name); note_launch(name);
   } else if (p.n >= 128 && !column) {
+    // one warp per whole row: the chunk kernel's apply pass with a single chunk and no carry-in
+    // (128-bit loads, 4 in flight per lane, when the row is unit-stride and 16-byte aligned)
+    ScPlan q = p;
+    q.nchunks = 1; q.chunk = (p.n + SC_CHUNK - 1) / SC_CHUNK * SC_CHUNK; q.carry = nullptr;
     int64_t g = (p.nrows + 7) / 8;
-    if (g > cap) g = cap;
-    scan_warp_kernel<T, O, PROD><<<(int)g, 256, 0, s>>>(p);
+    if (g > cap * 4) g = cap * 4;
+    scan_chunk_kernel<T, O, PROD, true><<<(int)g, 256, 0, s>>>(q);
   } else {
     int64_t g = (p.nrows + 255) / 256;
     if (g > cap) g = cap;
