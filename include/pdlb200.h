@@ -34,7 +34,7 @@ extern "C" {
 #define PDLB200_API
 #endif
 
-#define PDLB200_ABI_VERSION 2
+#define PDLB200_ABI_VERSION 3
 
 /* Element types: numeric values are PDL's own pdl_datatypes enum
  * (lib/PDL/Types.pm:27-255, order is significant for promotion).
@@ -89,11 +89,17 @@ enum {
   /* inner, lib/PDL/Primitive.pd:48-70 : a(n); b(n); [o]c() — c = sum_n a*b; n_size = ind[0],
    * inc_a_n = rinc[0], inc_b_n = rinc[1].  Any BAD element in the row makes c BAD. */
   PDLB200_OP_INNER = 76,
+  /* minmaximum, lib/PDL/Ufunc.pd:563-613 : a(n); [o]cmin(); [o]cmax(); indx [o]cmin_ind(); indx [o]cmax_ind()
+   * (the body of `minmax`, Ufunc.pd:738).  BAD and NaN elements are skipped; a row without any other element
+   * writes BAD to all four outputs and marks them BAD: `anybad` (required) reports that. */
+  PDLB200_OP_MINMAXIMUM = 77,
+  /* magnover, lib/PDL/Ufunc.pd:1235-1256 : a(n); real [o]b() — sqrt(sum_n a*a), BAD elements skipped */
+  PDLB200_OP_MAGNOVER = 78,
   PDLB200_OP__END
 };
 
 #define PDLB200_MAXDIMS 16  /* broadcast dims carried per call (pdl_broadcast.ndims) */
-#define PDLB200_MAXPDLS 4   /* parameters per transformation on this path (<= 3 used) */
+#define PDLB200_MAXPDLS 5   /* parameters per transformation on this path (minmaximum has 5) */
 
 /* pdlb200_par.flags */
 #define PDLB200_PAR_BADFLAG 1  /* pdl->state & PDL_BADVAL                  pdl.h.PL:560-561 */
@@ -132,7 +138,8 @@ typedef struct pdlb200_trans {
   double  param;     /* the OtherPars double of setvaltobad (value) / setbadtoval (newval): $COMP(...) */
   /* set{nan,inf,nonfinite}tobad mark their output BAD only if they wrote a BAD value (`if (flag)
    * $PDLSTATESETBAD(b)`, lib/PDL/Bad.pd:695-707).  Those three ops REQUIRE a host pointer here; the
-   * call synchronises the stream and stores 1/0.  Ignored by every other op. */
+   * call synchronises the stream and stores 1/0.  minmaximum uses it the same way for "a row had no
+   * usable element" (Ufunc.pd:578-583).  Ignored by every other op. */
   int32_t *anybad;
 } pdlb200_trans;
 

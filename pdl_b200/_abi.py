@@ -9,7 +9,7 @@ import ctypes as C
 from pathlib import Path
 
 MAXDIMS = 16
-MAXPDLS = 4
+MAXPDLS = 5
 PAR_BADFLAG = 1
 PAR_BADNAN = 2
 
@@ -62,9 +62,9 @@ OPS = {
     "matmult": 60, "converttype": 61, "ipow": 62,
     "isbad": 63, "isgood": 64, "isnan": 65, "setbadif": 66, "setvaltobad": 67,
     "setnantobad": 68, "setinftobad": 69, "setnonfinitetobad": 70, "setbadtonan": 71,
-    "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76,
+    "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76, "minmaximum": 77, "magnover": 78,
 }
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/pdlb200.h declares (tests check the .so exports them all)
 SYMBOLS = [

@@ -98,6 +98,7 @@ static void init_names() {
   N(PDLB200_OP_SETINFTOBAD, "setinftobad") N(PDLB200_OP_SETNONFINITETOBAD, "setnonfinitetobad")
   N(PDLB200_OP_SETBADTONAN, "setbadtonan") N(PDLB200_OP_SETBADTOVAL, "setbadtoval") N(PDLB200_OP_BADMASK, "badmask")
   N(PDLB200_OP_COPYBAD, "copybad") N(PDLB200_OP_AXISVALUES, "axisvalues") N(PDLB200_OP_INNER, "inner")
+  N(PDLB200_OP_MINMAXIMUM, "minmaximum") N(PDLB200_OP_MAGNOVER, "magnover")
 #undef N
 }
 
@@ -187,6 +188,8 @@ int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
   if (t->op >= PDLB200_OP_CUMUSUMOVER && t->op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (t->op >= PDLB200_OP_SUMOVER && t->op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (t->op == PDLB200_OP_INNER) return launch_inner(t, E);
+  if (t->op == PDLB200_OP_MINMAXIMUM) return launch_minmaximum(t, E);
+  if (t->op == PDLB200_OP_MAGNOVER) return launch_magnover(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
 }
 int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
@@ -202,6 +205,8 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT || op == PDLB200_OP_IPOW ||
       (op >= PDLB200_OP_ISBAD && op <= PDLB200_OP_AXISVALUES)) return launch_elementwise(t, E);
   if (op == PDLB200_OP_INNER) return launch_inner(t, E);
+  if (op == PDLB200_OP_MINMAXIMUM) return launch_minmaximum(t, E);
+  if (op == PDLB200_OP_MAGNOVER) return launch_magnover(t, E);
   if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);

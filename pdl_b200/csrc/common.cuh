@@ -109,6 +109,8 @@ int launch_ipow(const pdlb200_trans *t, const Err &E);
 int launch_badops(const pdlb200_trans *t, const Err &E);
 int launch_axisvalues(const pdlb200_trans *t, const Err &E);
 int launch_inner(const pdlb200_trans *t, const Err &E);
+int launch_magnover(const pdlb200_trans *t, const Err &E);
+int launch_minmaximum(const pdlb200_trans *t, const Err &E);
 int launch_reduce(const pdlb200_trans *t, const Err &E);
 int launch_scan(const pdlb200_trans *t, const Err &E);
 int launch_matmult(const pdlb200_trans *t, const Err &E);

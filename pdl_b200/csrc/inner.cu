@@ -95,13 +95,35 @@ __device__ __forceinline__ void in_row_offsets(const InPlan &p, int64_t row, int
   }
 }
 
-template <class T>
+// MAGN = magnover (lib/PDL/Ufunc.pd:1235-1256): b = a, BAD elements are SKIPPED (acc.bad then counts the good
+// ones), a row without a good element is BAD, and the result is sum == 0 ? 0 : sqrt(sum).
+template <class T, bool MAGN>
 __device__ __forceinline__ void in_write(const InPlan &p, T *out, const InAcc<T> &acc) {
-  *out = (p.badmode && acc.bad) ? from_bits<T>(p.cbad) : acc.result();
+  if constexpr (MAGN) {
+    if (p.badmode && !acc.bad) { *out = from_bits<T>(p.cbad); return; }
+    if constexpr (tt<T>::is_int) *out = acc.result();
+    else {
+      double sum;
+      if constexpr (sizeof(T) == 8) sum = acc.s + acc.c; else sum = acc.s;
+      *out = sum == 0 ? T(0) : (T)sqrt(sum);
+    }
+  } else {
+    *out = (p.badmode && acc.bad) ? from_bits<T>(p.cbad) : acc.result();
+  }
+}
+template <class T, bool MAGN>
+__device__ __forceinline__ void in_elem(const InPlan &p, InAcc<T> &acc, T va, T vb, T abad, T bbad) {
+  if constexpr (MAGN) {
+    if (p.badmode && is_bad(va, abad, p.abadnan != 0)) return;
+    acc.bad = 1; acc.add(va, va);
+  } else {
+    if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
+    else acc.add(va, vb);
+  }
 }
 
 // one warp per (row, chunk)
-template <class T>
+template <class T, bool MAGN>
 __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__ InPlan p) {
   const T abad = from_bits<T>(p.abad), bbad = from_bits<T>(p.bbad);
   const int lane = threadIdx.x & 31;
@@ -124,16 +146,12 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
       for (int64_t v0 = 0; v0 < nvec; v0 += 32 * U) {
         Pack<T> ra[U], rb[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) { const int64_t j = v0 + u * 32 + lane; if (j < nvec) { ra[u].q = qa[j]; rb[u].q = qb[j]; } }
+        for (int u = 0; u < U; u++) { const int64_t j = v0 + u * 32 + lane; if (j < nvec) { ra[u].q = qa[j]; if (!MAGN) rb[u].q = qb[j]; } }
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (v0 + u * 32 + lane < nvec) {
 #pragma unroll
-            for (int k = 0; k < VEC; k++) {
-              const T va = ra[u].e[k], vb = rb[u].e[k];
-              if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
-              else acc.add(va, vb);
-            }
+            for (int k = 0; k < VEC; k++) in_elem<T, MAGN>(p, acc, ra[u].e[k], MAGN ? ra[u].e[k] : rb[u].e[k], abad, bbad);
           }
         }
       }
@@ -147,30 +165,26 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
 #pragma unroll
       for (int u = 0; u < U; u++) {
         va[u] = a_const ? a0 : pa[(n + u * 32) * p.inc_a];
-        vb[u] = b_const ? b0 : pb[(n + u * 32) * p.inc_b];
+        vb[u] = MAGN ? va[u] : (b_const ? b0 : pb[(n + u * 32) * p.inc_b]);
       }
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (p.badmode && (is_bad(va[u], abad, p.abadnan != 0) || is_bad(vb[u], bbad, p.bbadnan != 0))) acc.bad = 1;
-        else acc.add(va[u], vb[u]);
-      }
+      for (int u = 0; u < U; u++) in_elem<T, MAGN>(p, acc, va[u], vb[u], abad, bbad);
     }
     for (; n < hi; n += 32) {
-      const T va = a_const ? a0 : pa[n * p.inc_a], vb = b_const ? b0 : pb[n * p.inc_b];
-      if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
-      else acc.add(va, vb);
+      const T va = a_const ? a0 : pa[n * p.inc_a], vb = MAGN ? va : (b_const ? b0 : pb[n * p.inc_b]);
+      in_elem<T, MAGN>(p, acc, va, vb, abad, bbad);
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const InAcc<T> o = shfl_down_acc(acc, d); acc.merge(o); }
     if (lane == 0) {
-      if (p.nchunks == 1) in_write<T>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+      if (p.nchunks == 1) in_write<T, MAGN>(p, reinterpret_cast<T *>(p.c) + oc, acc);
       else reinterpret_cast<InAcc<T> *>(p.part)[w] = acc;
     }
   }
 }
 
 // finishing pass: one warp per row merges the chunk partials (lanes stride over the chunks, then a shuffle tree)
-template <class T>
+template <class T, bool MAGN>
 __global__ void __launch_bounds__(256) inner_finish_kernel(const __grid_constant__ InPlan p) {
   const int lane = threadIdx.x & 31;
   for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.nrows; row += (int64_t)gridDim.x * 8) {
@@ -181,12 +195,12 @@ __global__ void __launch_bounds__(256) inner_finish_kernel(const __grid_constant
     for (int64_t k = lane; k < p.nchunks; k += 32) acc.merge(part[k]);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const InAcc<T> o = shfl_down_acc(acc, d); acc.merge(o); }
-    if (lane == 0) in_write<T>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+    if (lane == 0) in_write<T, MAGN>(p, reinterpret_cast<T *>(p.c) + oc, acc);
   }
 }
 
 // many short rows: one thread per row
-template <class T>
+template <class T, bool MAGN>
 __global__ void __launch_bounds__(256) inner_thread_kernel(const __grid_constant__ InPlan p) {
   const T abad = from_bits<T>(p.abad), bbad = from_bits<T>(p.bbad);
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (int64_t)gridDim.x * blockDim.x) {
@@ -196,21 +210,21 @@ __global__ void __launch_bounds__(256) inner_thread_kernel(const __grid_constant
     const T *pb = reinterpret_cast<const T *>(p.b) + ob;
     InAcc<T> acc; acc.init();
     for (int64_t n = 0; n < p.n; n++) {
-      const T va = pa[n * p.inc_a], vb = pb[n * p.inc_b];
-      if (p.badmode && (is_bad(va, abad, p.abadnan != 0) || is_bad(vb, bbad, p.bbadnan != 0))) acc.bad = 1;
-      else acc.add(va, vb);
+      const T va = pa[n * p.inc_a], vb = MAGN ? va : pb[n * p.inc_b];
+      in_elem<T, MAGN>(p, acc, va, vb, abad, bbad);
     }
-    in_write<T>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+    in_write<T, MAGN>(p, reinterpret_cast<T *>(p.c) + oc, acc);
   }
 }
 
-template <class T>
+template <class T, bool MAGN = false>
 static int inner_go(InPlan &p, cudaStream_t s, const Err &E) {
+  const char *name = MAGN ? "magnover" : "inner";
   const int64_t cap = (int64_t)sm_count() * 8;
   if (p.n < 64 && p.nrows >= 1024) {
     int64_t g = (p.nrows + 255) / 256;
     if (g > cap) g = cap;
-    inner_thread_kernel<T><<<(int)g, 256, 0, s>>>(p);
+    inner_thread_kernel<T, MAGN><<<(int)g, 256, 0, s>>>(p);
   } else {
     // about one resident wave of warps (64 per SM) over all rows; chunks are multiples of 1024 elements
     int64_t want = cap * 8 / (p.nrows > 0 ? p.nrows : 1);
@@ -226,15 +240,15 @@ static int inner_go(InPlan &p, cudaStream_t s, const Err &E) {
     }
     int64_t g = (p.nrows * p.nchunks + 7) / 8;
     if (g > cap * 4) g = cap * 4;
-    inner_warp_kernel<T><<<(int)g, 256, 0, s>>>(p);
+    inner_warp_kernel<T, MAGN><<<(int)g, 256, 0, s>>>(p);
     if (p.nchunks > 1) {
       int64_t g2 = (p.nrows + 7) / 8;
       if (g2 > cap) g2 = cap;
-      inner_finish_kernel<T><<<(int)g2, 256, 0, s>>>(p);
-      note_launch("inner");
+      inner_finish_kernel<T, MAGN><<<(int)g2, 256, 0, s>>>(p);
+      note_launch(name);
     }
   }
-  note_launch("inner");
+  note_launch(name);
   PDLB200_CUDA_OK(cudaGetLastError(), E);
   return PDLB200_OK;
 }
@@ -272,5 +286,33 @@ int launch_inner(const pdlb200_trans *t, const Err &E) {
     default: break;
   }
   return E.fail(PDLB200_EUNSUPPORTED, "inner: type %d is not on the device path", t->datatype);
+}
+
+// magnover, lib/PDL/Ufunc.pd:1235-1256 : a(n); real [o]b().  GenericTypes D LD C* F ("F last"), so integer input
+// is converted to float by the caller; device types F and D.  The reference sums a*a in long double and takes
+// sqrtl; here the float sum is carried in double and the double sum in a compensated pair (see above).
+int launch_magnover(const pdlb200_trans *t, const Err &E) {
+  if (t->npdls != 2) return E.fail(PDLB200_EINVAL, "magnover: expected 2 parameters");
+  if (t->datatype != PDLB200_F && t->datatype != PDLB200_D)
+    return E.fail(PDLB200_EUNSUPPORTED, "magnover: type %d is not on the device path (float and double are)", t->datatype);
+  const size_t sz = pdlb200_type_size(t->datatype);
+  Collapsed c;
+  collapse_dims(t, &c);
+  if (c.total == 0) return PDLB200_OK;
+  if (c.nd > MAXD) return E.fail(PDLB200_EUNSUPPORTED, "magnover: %d non-mergeable broadcast dims exceed the device walker's %d", c.nd, MAXD);
+  InPlan p{};
+  p.n = t->ind[0]; p.inc_a = p.inc_b = t->rinc[0];
+  if (p.n < 0) return E.fail(PDLB200_EINVAL, "magnover: n = %lld", (long long)p.n);
+  if ((!t->pdls[0].data && p.n > 0) || !t->pdls[1].data) return E.fail(PDLB200_EINVAL, "magnover: NULL data");
+  p.a = p.b = (const char *)t->pdls[0].data + t->pdls[0].offs * (int64_t)sz;
+  p.c = (char *)t->pdls[1].data + t->pdls[1].offs * (int64_t)sz;
+  p.nd = c.nd; p.nrows = c.total; p.nchunks = 1;
+  for (int d = 0; d < c.nd; d++) { p.dims[d] = c.dims[d]; p.sa[d] = p.sb[d] = c.st[0][d]; p.sc[d] = c.st[1][d]; }
+  p.abad = p.bbad = t->pdls[0].badval; p.cbad = t->pdls[1].badval;
+  p.badmode = t->bvalflag != 0;
+  p.abadnan = p.bbadnan = (t->pdls[0].flags & PDLB200_PAR_BADNAN) != 0;
+  cudaStream_t s = (cudaStream_t)t->stream;
+  if (t->datatype == PDLB200_F) return inner_go<float, true>(p, s, E);
+  return inner_go<double, true>(p, s, E);
 }
 }  // namespace pdlb200

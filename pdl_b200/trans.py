@@ -53,7 +53,8 @@ _AF = (T.F, T.LD) + T.COMPLEX + (T.D,)
 # what the op's Code does to the output state after make_trans_mutual propagated the input flags
 _STATE_SETBAD = ("setbadif", "setvaltobad")                       # $PDLSTATESETBAD(b), unconditionally
 _STATE_SETGOOD = ("setbadtonan", "setbadtoval", "badmask")        # $PDLSTATESETGOOD(b)
-_STATE_IFFLAG = ("setnantobad", "setinftobad", "setnonfinitetobad")  # if (flag) $PDLSTATESETBAD(b)
+_STATE_IFFLAG = ("setnantobad", "setinftobad", "setnonfinitetobad",  # if (flag) $PDLSTATESETBAD(b)
+                 "minmaximum")                                       # a row without a usable element (Ufunc.pd:578-583)
 
 
 def _bi(name, gentypes, kind="biop"):
@@ -89,6 +90,10 @@ SPECS = {s.name: s for s in [
     _rd("minimum_ind", _R, T.IND), _rd("maximum_ind", _R, T.IND),
     _rd("andover", _A), _rd("orover", _A), _rd("zcover", _A), _rd("xorover", _A),
     _rd("bandover", _I), _rd("borover", _I), _rd("bxorover", _I),
+    # minmaximum, lib/PDL/Ufunc.pd:563-613 (the body of minmax, :738); magnover, :1235-1256 (GenericTypes "F last")
+    OpSpec("minmaximum", [Par("a", ("n",)), Par("cmin", out=True), Par("cmax", out=True),
+                          Par("cmin_ind", out=True, typed=T.IND), Par("cmax_ind", out=True, typed=T.IND)], _R, "reduce"),
+    OpSpec("magnover", [Par("a", ("n",)), Par("b", out=True)], (T.D, T.LD) + T.COMPLEX + (T.F,), "reduce"),
     # lib/PDL/Bad.pd:418-480
     _rd("nbadover", _A, T.IND), _rd("ngoodover", _A, T.IND),
     # scans, lib/PDL/Ufunc.pd:120-141 : a(n); [o]b(n)

@@ -7,7 +7,7 @@ from .trans import run_op, as_pdl
 _REDUCERS = ["sumover", "prodover", "dsumover", "dprodover", "average", "daverage",
              "minimum", "maximum", "minimum_ind", "maximum_ind",
              "andover", "orover", "zcover", "xorover", "bandover", "borover", "bxorover",
-             "nbadover", "ngoodover", "cumusumover", "cumuprodover", "dcumusumover", "dcumuprodover"]
+             "nbadover", "ngoodover", "cumusumover", "cumuprodover", "dcumusumover", "dcumuprodover", "magnover"]
 
 
 def _mk(name):
@@ -46,4 +46,18 @@ def _mk_whole(name, over):
 for _n, _o in _WHOLE.items():
     globals()[_n] = _mk_whole(_n, _o)
 
-__all__ = _REDUCERS + list(_WHOLE) + ["avgover", "davgover", "minover", "maxover", "minover_ind", "maxover_ind"]
+def minmaximum(a, cmin=None, cmax=None, cmin_ind=None, cmax_ind=None):
+    """PDL::minmaximum(a(n); [o]cmin(); [o]cmax(); indx [o]cmin_ind(); indx [o]cmax_ind()) — Ufunc.pd:563-613."""
+    return tuple(run_op("minmaximum", [as_pdl(a)], [cmin, cmax, cmin_ind, cmax_ind]))
+
+
+minmaxover = minmaximum
+
+
+def minmax(a):
+    """PDL::minmax (Ufunc.pd:738): map $_->sclr, ($x->flat->minmaximum)[0,1]"""
+    r = minmaximum(as_pdl(a).flat())
+    return r[0].sclr(), r[1].sclr()
+
+
+__all__ = ["minmaximum", "minmaxover", "minmax"] + _REDUCERS + list(_WHOLE) + ["avgover", "davgover", "minover", "maxover", "minover_ind", "maxover_ind"]

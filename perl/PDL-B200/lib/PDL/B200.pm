@@ -26,7 +26,8 @@ our %OPS = (
   'PDL::Ufunc' => { sumover=>30, prodover=>31, dsumover=>32, dprodover=>33, average=>34, daverage=>35,
     minimum=>36, maximum=>37, minimum_ind=>38, maximum_ind=>39, andover=>40, orover=>41,
     bandover=>42, borover=>43, zcover=>44, xorover=>45, bxorover=>46,
-    cumusumover=>50, cumuprodover=>51, dcumusumover=>52, dcumuprodover=>53 },
+    cumusumover=>50, cumuprodover=>51, dcumusumover=>52, dcumuprodover=>53,
+    minmaximum=>77, magnover=>78 },
   'PDL::Bad' => { nbadover=>47, ngoodover=>48, isbad=>63, isgood=>64, isnan=>65, setbadif=>66, setvaltobad=>67,
     setnantobad=>68, setinftobad=>69, setnonfinitetobad=>70, setbadtonan=>71, setbadtoval=>72, badmask=>73,
     copybad=>74 },

@@ -199,6 +199,9 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
     tr->pdls[npdls - 1]->state |= PDL_BADVAL;
   else if (opid == PDLB200_OP_SETBADTONAN || opid == PDLB200_OP_SETBADTOVAL || opid == PDLB200_OP_BADMASK)
     tr->pdls[npdls - 1]->state &= ~PDL_BADVAL;
+  /* minmaximum: a row without a usable element marks all four outputs BAD (Ufunc.pd:578-583) */
+  if (opid == PDLB200_OP_MINMAXIMUM && anybad)
+    for (j = vt->nparents; j < npdls; j++) tr->pdls[j]->state |= PDL_BADVAL;
   pdlb200_pp_device_calls++;
   if (pdlb200_pp_verbose) fprintf(stderr, "PDL::B200 %s -> %s\n", vt->name, pdlb200_last_kernel());
   return PDL_err;

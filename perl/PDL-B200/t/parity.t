@@ -78,6 +78,12 @@ for my $t (@types) {
   both("sequence $t",     sub { sequence($t, 301, 5) });
   both("inner $t",        sub { inner($a % 3, $b % 3) });
   both("inner bad $t",    sub { inner($bad % 3, $b % 3) });
+  for my $k (0 .. 3) {
+    both("minmaximum[$k] $t",     sub { ($a->minmaximum)[$k] });
+    both("bad minmaximum[$k] $t", sub { ($bad->minmaximum)[$k] });
+  }
+  is_deeply([do { PDL::B200::enable(1); $a->minmax }], [do { PDL::B200::enable(0); my @r = $a->minmax; PDL::B200::enable(1); @r }], "minmax $t");
+  both("magnover $t",     sub { ($a % 5)->magnover });
   if (!$t->integer) {
     my $sp = $a->copy; $sp->set(3, 1, 'nan'); $sp->set(4, 2, 'inf');
     both("setnantobad $t",       sub { $sp->setnantobad });

@@ -125,10 +125,13 @@ sub add_case {
       $out = defined $call->{type} ? sequence($TOBJ{$call->{type}}, @{$call->{dims}}) : sequence(@{$call->{dims}});
     } elsif ($kind eq 'inner') {
       $out = PDL::inner($args[0], $args[1]);
+    } elsif ($kind eq 'minmaximum') {   # four outputs
+      $out = [ $args[0]->minmaximum ];
     } else { die "kind $kind" }
     1;
   };
   if (!$ok) { my $e = $@; $e =~ s/\s+at \S+ line \d+.*//s; push @cases, { name => $name, inputs => \@specs, call => $call, error => $e }; return; }
+  if (ref $out eq 'ARRAY') { push @cases, { name => $name, inputs => \@specs, call => $call, outputs => [map out_of($_), @$out] }; return; }
   push @cases, { name => $name, inputs => \@specs, call => $call, output => out_of($out), (defined $tol ? (tol_ulp => $tol) : ()) };
 }
 sub flush_cases {
@@ -426,3 +429,27 @@ for my $t (@TYPES) {
 }
 add_case("inner-mismatch", [[mk('double',[3],'small')],[mk('double',[4],'small')]], {kind=>'inner'});
 flush_cases('inner.json');
+
+# ---------------------------------------------------------------- minmaximum (Ufunc.pd:563-613), magnover (:1235-1256)
+for my $t (@TYPES) {
+  add_case("minmaximum-$t", [[mk($t,[13,4],'small')]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-mixed-3d", [[mk($t,[6,3,4],'mixed')]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-long-flat", [[mk($t,[3000],'mixed')]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-strided", [[mk($t,[24,3],'small'), [['slice','-1:0:-2,:']]]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-bad", [[with_bad(mk($t,[9,4],'small'), 0, 3, 8, (map { 18 + $_ } 0..8), 30)]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-empty-n", [[mk($t,[0,3],'small')]], {kind=>'minmaximum'});
+  add_case("minmaximum-$t-ties", [[pdl($TOBJ{$t}, [[3,1,1,3,2],[5,5,5,5,5]])]], {kind=>'minmaximum'});
+}
+for my $t (qw(float double)) {
+  my $rows = pdl($TOBJ{$t}, [[$NAN,1,2],[1,$NAN,2],[1,2,$NAN],[$NAN,$NAN,$NAN],[0,-0.0,0],[-0.0,0,-0.0],[$INF,-$INF,5],[3,3,3]]);
+  add_case("minmaximum-$t-nan-zero", [[$rows]], {kind=>'minmaximum'});
+  my $rb = $rows->copy; $rb->badflag(1); $rb->badvalue($NAN);
+  add_case("minmaximum-$t-nan-badvalue", [[$rb]], {kind=>'minmaximum'});
+  add_case("magnover-$t", [[mk($t,[13,4],'small')]], {kind=>'reduce', op=>'magnover'}, 1);
+  add_case("magnover-$t-345", [[pdl($TOBJ{$t}, [[3,4],[0,0],[5,12],[-8,15]])]], {kind=>'reduce', op=>'magnover'}, 0);
+  add_case("magnover-$t-bad", [[with_bad(mk($t,[9,4],'small'), 0, 3, 8, (map { 18 + $_ } 0..8), 30)]], {kind=>'reduce', op=>'magnover'}, 1);
+  add_case("magnover-$t-long", [[mk($t,[5000,2],'small')]], {kind=>'reduce', op=>'magnover'}, 1);
+  add_case("magnover-$t-empty-n", [[mk($t,[0,3],'small')]], {kind=>'reduce', op=>'magnover'});
+}
+add_case("magnover-long-to-float", [[mk('long',[7,2],'small')]], {kind=>'reduce', op=>'magnover'}, 1);
+flush_cases('minmax.json');

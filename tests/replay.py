@@ -70,6 +70,8 @@ def run_call(call, args):
         return basic.sequence(TYPE_ID[call["type"]] if call.get("type") else None, *call["dims"], engine=call["_engine"])
     if kind == "inner":
         return P.inner(args[0], args[1])
+    if kind == "minmaximum":
+        return list(ufunc.minmaximum(args[0]))
     raise ValueError(kind)
 
 
@@ -109,6 +111,15 @@ def check_case(case, engine):
             return
         raise AssertionError(f"{case['name']}: reference raised {case['error']!r}, we did not")
     out = run_call(case["call"], args)
+    if "outputs" in case:
+        assert len(out) == len(case["outputs"])
+        for k, (o, want) in enumerate(zip(out, case["outputs"])):
+            assert o.type == want["type"], (case["name"], k, o.type, want["type"])
+            assert o.dims == want["dims"], (case["name"], k, o.dims, want["dims"])
+            assert int(o.badflag) == want["badflag"], (case["name"], k, "badflag", o.badflag, want["badflag"])
+            exp = np.frombuffer(bytes.fromhex(want["hex"]), dtype=T.NP_DTYPE[o.datatype])
+            assert o.to_numpy().reshape(-1).tobytes() == exp.tobytes(), (case["name"], k, o.to_numpy(), exp)
+        return
     want = case["output"]
     assert out.type == want["type"], (case["name"], out.type, want["type"])
     assert out.dims == want["dims"], (case["name"], out.dims, want["dims"])

@@ -24,12 +24,12 @@ def test_header_symbols_all_exported():
 def test_struct_layout_matches_header():
     # sizes computed from the header's field list (LP64)
     assert C.sizeof(_abi.Par) == 8 + 8 + 8 + 4 + 4
-    assert C.sizeof(_abi.Trans) == 6 * 4 + 16 * 8 + 64 * 8 + 4 * 8 + 8 * 8 + 4 * C.sizeof(_abi.Par) + 8 + 8 + 8
+    assert C.sizeof(_abi.Trans) == 6 * 4 + 16 * 8 + 80 * 8 + 4 * 8 + 8 * 8 + 5 * C.sizeof(_abi.Par) + 8 + 8 + 8
 
 
 def test_plumbing_without_gpu():
     lib = _abi.load()
-    assert lib.pdlb200_abi_version() == 2
+    assert lib.pdlb200_abi_version() == 3
     assert lib.pdlb200_type_size(10) == 8 and lib.pdlb200_type_size(0) == 1
     assert lib.pdlb200_op_name(30) == b"sumover"
     if lib.pdlb200_device_count() > 0:

@@ -401,3 +401,49 @@ def test_inner_double_random_within_tolerance(engines):
     af, bf = a.astype(np.float32), b.astype(np.float32)
     (ga, oa), (gb, ob) = both(engines, af, T.F), both(engines, bf, T.F)
     assert_same("inner-float-random", P.inner(ga, gb), P.inner(oa, ob), tol_ulp=1)
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_minmaximum(engines, t):
+    rng = np.random.default_rng(1100 + t)
+    for shape in ((3, 70_001), (2000, 33), (5, 4097), (1, 300_007)):
+        a = rand_array(rng, t, shape, "small" if shape[1] > 1000 else "mixed")   # small: many ties -> first index must win
+        (ga, oa) = both(engines, a, t)
+        for k, (g, o) in enumerate(zip(ufunc.minmaximum(ga), ufunc.minmaximum(oa))):
+            assert_same(f"minmaximum[{k}]-{T.NAMES[t]}-{shape}", g, o)
+        ab = a.copy()
+        ab[rng.random(shape) < 0.3] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        ab[0, :] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])           # an all-BAD row
+        (gb, ob) = both(engines, ab, t, True)
+        for k, (g, o) in enumerate(zip(ufunc.minmaximum(gb), ufunc.minmaximum(ob))):
+            assert_same(f"minmaximum-bad[{k}]-{T.NAMES[t]}-{shape}", g, o)
+        # strided / transposed view
+        for k, (g, o) in enumerate(zip(ufunc.minmaximum(ga.xchg(0, 1)), ufunc.minmaximum(oa.xchg(0, 1)))):
+            assert_same(f"minmaximum-xchg[{k}]-{T.NAMES[t]}-{shape}", g, o)
+    if t in (T.F, T.D):
+        a = rand_array(rng, t, (64, 5000))
+        a[rng.random(a.shape) < 0.2] = np.nan
+        a[3, :] = np.nan                                   # all-NaN row: BAD outputs + badflag without any BAD input
+        a[5, ::2] = 0.0; a[5, 1::2] = -0.0
+        (ga, oa) = both(engines, a, t)
+        for k, (g, o) in enumerate(zip(ufunc.minmaximum(ga), ufunc.minmaximum(oa))):
+            assert_same(f"minmaximum-nan[{k}]-{T.NAMES[t]}", g, o)
+        assert ufunc.minmaximum(ga)[0].badflag
+        assert ufunc.minmax(ga) == ufunc.minmax(oa)
+
+
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_magnover(engines, t):
+    rng = np.random.default_rng(1200 + t)
+    for shape in ((3, 70_001), (2000, 33), (1, 300_007)):
+        a = rand_array(rng, t, shape)
+        (ga, oa) = both(engines, a, t)
+        assert_same(f"magnover-{T.NAMES[t]}-{shape}", ufunc.magnover(ga), ufunc.magnover(oa), tol_ulp=1)
+        ab = a.copy(); ab[rng.random(shape) < 0.3] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        ab[0, :] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        (gb, ob) = both(engines, ab, t, True)
+        assert_same(f"magnover-bad-{T.NAMES[t]}-{shape}", ufunc.magnover(gb), ufunc.magnover(ob), tol_ulp=1)
+    # exactly representable: 3-4-5 style rows must be bit-exact
+    a = np.array([[3, 4] * 500, [5, 12] * 500, [0, 0] * 500], dtype=T.NP_DTYPE[t])
+    (ga, oa) = both(engines, a, t)
+    assert_same(f"magnover-exact-{T.NAMES[t]}", ufunc.magnover(ga), ufunc.magnover(oa))
