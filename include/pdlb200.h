@@ -95,6 +95,9 @@ enum {
   PDLB200_OP_MINMAXIMUM = 77,
   /* magnover, lib/PDL/Ufunc.pd:1235-1256 : a(n); real [o]b() — sqrt(sum_n a*a), BAD elements skipped */
   PDLB200_OP_MAGNOVER = 78,
+  /* outer, lib/PDL/Primitive.pd:78-96 : a(n); b(m); [o]c(n,m) — c = a*b; ind = {n, m},
+   * rinc = {inc_a_n, inc_b_m, inc_c_n, inc_c_m}.  Runs as mult over two extra leading broadcast dims. */
+  PDLB200_OP_OUTER = 79,
   PDLB200_OP__END
 };
 

@@ -9,9 +9,9 @@ from .engine import CudaEngine, Engine, PDLError, default_engine, set_default_en
 from .core import PDL, pdl, zeroes, ones, sequence, null
 from .trans import run_op, prepare_op, Prepared, run_biop, run_ufunc, as_pdl, convert_type, SPECS
 from . import ops, ufunc, primitive, bad, basic
-from .primitive import matmult, inner
+from .primitive import matmult, inner, outer
 
 __all__ = ["PDL", "pdl", "zeroes", "ones", "sequence", "null", "PDLError", "CudaEngine", "Engine",
            "default_engine", "set_default_engine", "run_op", "prepare_op", "Prepared", "run_biop", "run_ufunc", "as_pdl",
-           "convert_type", "SPECS", "ops", "ufunc", "primitive", "bad", "basic", "matmult", "inner", "types",
+           "convert_type", "SPECS", "ops", "ufunc", "primitive", "bad", "basic", "matmult", "inner", "outer", "types",
            "SB", "B", "S", "US", "L", "UL", "IND", "ULL", "LL", "F", "D"]

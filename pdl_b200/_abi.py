@@ -62,7 +62,7 @@ OPS = {
     "matmult": 60, "converttype": 61, "ipow": 62,
     "isbad": 63, "isgood": 64, "isnan": 65, "setbadif": 66, "setvaltobad": 67,
     "setnantobad": 68, "setinftobad": 69, "setnonfinitetobad": 70, "setbadtonan": 71,
-    "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76, "minmaximum": 77, "magnover": 78,
+    "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76, "minmaximum": 77, "magnover": 78, "outer": 79,
 }
 ABI_VERSION = 3
 

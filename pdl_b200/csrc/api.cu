@@ -98,7 +98,7 @@ static void init_names() {
   N(PDLB200_OP_SETINFTOBAD, "setinftobad") N(PDLB200_OP_SETNONFINITETOBAD, "setnonfinitetobad")
   N(PDLB200_OP_SETBADTONAN, "setbadtonan") N(PDLB200_OP_SETBADTOVAL, "setbadtoval") N(PDLB200_OP_BADMASK, "badmask")
   N(PDLB200_OP_COPYBAD, "copybad") N(PDLB200_OP_AXISVALUES, "axisvalues") N(PDLB200_OP_INNER, "inner")
-  N(PDLB200_OP_MINMAXIMUM, "minmaximum") N(PDLB200_OP_MAGNOVER, "magnover")
+  N(PDLB200_OP_MINMAXIMUM, "minmaximum") N(PDLB200_OP_MAGNOVER, "magnover") N(PDLB200_OP_OUTER, "outer")
 #undef N
 }
 
@@ -129,7 +129,7 @@ int ew_unary(const pdlb200_trans *, const Err &);
 
 int launch_elementwise(const pdlb200_trans *t, const Err &E) {
   const int op = t->op;
-  if (op <= PDLB200_OP_DIVIDE) return ew_arith(t, E);
+  if (op <= PDLB200_OP_DIVIDE || op == PDLB200_OP_OUTER) return ew_arith(t, E);
   if (op <= PDLB200_OP_NE) return ew_cmp(t, E);
   if (op <= PDLB200_OP_XOR || op == PDLB200_OP_BITNOT) return ew_bits(t, E);
   if (op <= PDLB200_OP_SPACESHIP) return ew_func(t, E);
@@ -203,7 +203,7 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   if (int rc = validate(t, E)) return rc;
   const int op = t->op;
   if (op <= PDLB200_OP_ABS2 || op == PDLB200_OP_CONVERT || op == PDLB200_OP_IPOW ||
-      (op >= PDLB200_OP_ISBAD && op <= PDLB200_OP_AXISVALUES)) return launch_elementwise(t, E);
+      (op >= PDLB200_OP_ISBAD && op <= PDLB200_OP_AXISVALUES) || op == PDLB200_OP_OUTER) return launch_elementwise(t, E);
   if (op == PDLB200_OP_INNER) return launch_inner(t, E);
   if (op == PDLB200_OP_MINMAXIMUM) return launch_minmaximum(t, E);
   if (op == PDLB200_OP_MAGNOVER) return launch_magnover(t, E);

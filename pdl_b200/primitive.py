@@ -34,4 +34,10 @@ def inner(a, b, c=None) -> PDL:
     return run_op("inner", [a, as_pdl(b, a.engine)], [c])[0]
 
 
-__all__ = ["matmult", "inner"]
+def outer(a, b, c=None) -> PDL:
+    """PDL::outer(a(n); b(m); [o]c(n,m)) — lib/PDL/Primitive.pd:78-96."""
+    a = as_pdl(a)
+    return run_op("outer", [a, as_pdl(b, a.engine)], [c])[0]
+
+
+__all__ = ["matmult", "inner", "outer"]

@@ -120,6 +120,7 @@ SPECS = {s.name: s for s in [
     # axisvalues, lib/PDL/Primitive.pd:1468-1474; inner, :48-70
     OpSpec("axisvalues", [Par("i", ("n",)), Par("a", ("n",), out=True)], _A, "axis", inplace=("i",)),
     OpSpec("inner", [Par("a", ("n",)), Par("b", ("n",)), Par("c", out=True)], _A, "inner"),
+    OpSpec("outer", [Par("a", ("n",)), Par("b", ("m",)), Par("c", ("n", "m"), out=True)], _A, "outer"),
     # matmult, lib/PDL/Primitive.pd:191-195
     OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
 ]}
@@ -396,6 +397,9 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     elif spec.kind == "axis":
         i, a = placeholder
         named = {"ind": [ind["n"]], "rinc": [_real_inc(i, 0), _real_inc(a, 0)]}
+    elif spec.kind == "outer":
+        a, b, c = placeholder
+        named = {"ind": [ind["n"], ind["m"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0), _real_inc(c, 0), _real_inc(c, 1)]}
     elif spec.kind == "inner":
         a, b, _c = placeholder
         named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0)]}

@@ -31,7 +31,7 @@ our %OPS = (
   'PDL::Bad' => { nbadover=>47, ngoodover=>48, isbad=>63, isgood=>64, isnan=>65, setbadif=>66, setvaltobad=>67,
     setnantobad=>68, setinftobad=>69, setnonfinitetobad=>70, setbadtonan=>71, setbadtoval=>72, badmask=>73,
     copybad=>74 },
-  'PDL::Primitive' => { matmult=>60, axisvalues=>75, inner=>76 },
+  'PDL::Primitive' => { matmult=>60, axisvalues=>75, inner=>76, outer=>79 },
 );
 
 sub _libref {

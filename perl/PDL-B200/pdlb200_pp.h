@@ -161,6 +161,11 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
     /* ind_sizes are sorted by name: h, t, w ([gen] Primitive-pp-matmult.c); the ABI wants t, h, w */
     d.ind[0] = tr->ind_sizes[1]; d.ind[1] = tr->ind_sizes[0]; d.ind[2] = tr->ind_sizes[2];
     for (i = 0; i < 6; i++) d.rinc[i] = tr->inc_sizes[i];
+  } else if (opid == PDLB200_OP_OUTER) {
+    /* ind_names are sorted (pdl.h.PL:396): m, n; the ABI wants n, m.  inc_sizes follow the parameter order:
+     * a(n), b(m), c(n,m) = exactly rinc[0..3] */
+    d.ind[0] = tr->ind_sizes[1]; d.ind[1] = tr->ind_sizes[0];
+    for (i = 0; i < 4; i++) d.rinc[i] = tr->inc_sizes[i];
   } else if (vt->ninds >= 1) {
     d.ind[0] = tr->ind_sizes[0];
     for (i = 0; i < vt->nind_ids && i < 8; i++) d.rinc[i] = tr->inc_sizes[i];

@@ -84,6 +84,8 @@ for my $t (@types) {
   }
   is_deeply([do { PDL::B200::enable(1); $a->minmax }], [do { PDL::B200::enable(0); my @r = $a->minmax; PDL::B200::enable(1); @r }], "minmax $t");
   both("magnover $t",     sub { ($a % 5)->magnover });
+  both("outer $t",        sub { outer($a->slice(':,(1)') % 9, $b->slice('0:40,(2)') % 9) });
+  both("outer bad $t",    sub { outer($bad->slice(':,(0)') % 9, $b->slice('0:40,(2)') % 9) });
   if (!$t->integer) {
     my $sp = $a->copy; $sp->set(3, 1, 'nan'); $sp->set(4, 2, 'inf');
     both("setnantobad $t",       sub { $sp->setnantobad });

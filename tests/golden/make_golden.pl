@@ -125,6 +125,8 @@ sub add_case {
       $out = defined $call->{type} ? sequence($TOBJ{$call->{type}}, @{$call->{dims}}) : sequence(@{$call->{dims}});
     } elsif ($kind eq 'inner') {
       $out = PDL::inner($args[0], $args[1]);
+    } elsif ($kind eq 'outer') {
+      $out = PDL::outer($args[0], $args[1]);
     } elsif ($kind eq 'minmaximum') {   # four outputs
       $out = [ $args[0]->minmaximum ];
     } else { die "kind $kind" }
@@ -453,3 +455,13 @@ for my $t (qw(float double)) {
 }
 add_case("magnover-long-to-float", [[mk('long',[7,2],'small')]], {kind=>'reduce', op=>'magnover'}, 1);
 flush_cases('minmax.json');
+
+# ---------------------------------------------------------------- outer (Primitive.pd:78-96)
+for my $t (@TYPES) {
+  add_case("outer-$t", [[mk($t,[13],'small')],[mk($t,[7],'small')]], {kind=>'outer'});
+  add_case("outer-$t-broadcast", [[mk($t,[5,3],'small')],[mk($t,[4],'mixed')]], {kind=>'outer'});
+  add_case("outer-$t-bad", [[with_bad(mk($t,[9],'small'), 3)],[with_bad(mk($t,[6,2],'small'), 7)]], {kind=>'outer'});
+  add_case("outer-$t-strided", [[mk($t,[24],'small'), [['slice','-1:0:-2']]],[mk($t,[5,4],'small'), [['xchg',0,1]]]], {kind=>'outer'});
+}
+add_case("outer-empty", [[mk('double',[0],'small')],[mk('double',[3],'small')]], {kind=>'outer'});
+flush_cases('outer.json');

@@ -70,6 +70,8 @@ def run_call(call, args):
         return basic.sequence(TYPE_ID[call["type"]] if call.get("type") else None, *call["dims"], engine=call["_engine"])
     if kind == "inner":
         return P.inner(args[0], args[1])
+    if kind == "outer":
+        return P.outer(args[0], args[1])
     if kind == "minmaximum":
         return list(ufunc.minmaximum(args[0]))
     raise ValueError(kind)

@@ -447,3 +447,17 @@ def test_magnover(engines, t):
     a = np.array([[3, 4] * 500, [5, 12] * 500, [0, 0] * 500], dtype=T.NP_DTYPE[t])
     (ga, oa) = both(engines, a, t)
     assert_same(f"magnover-exact-{T.NAMES[t]}", ufunc.magnover(ga), ufunc.magnover(oa))
+
+
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_outer(engines, t):
+    rng = np.random.default_rng(1300 + t)
+    a, b = rand_array(rng, t, (3, 5001), "small"), rand_array(rng, t, (777,), "small")
+    (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+    assert_same(f"outer-{T.NAMES[t]}", P.outer(ga, gb), P.outer(oa, ob))
+    ab = a.copy(); ab[rng.random(a.shape) < 0.05] = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+    (gx, ox) = both(engines, ab, t, True)
+    assert_same(f"outer-bad-{T.NAMES[t]}", P.outer(gx, gb), P.outer(ox, ob))
+    # same numbers as the operator on dummy dims (what the reference's docs say outer is)
+    (g1, _), (g2, _) = both(engines, a[0], t), both(engines, b, t)
+    assert P.outer(g1, g2).to_numpy().tobytes() == (g1.dummy(1, 1) * g2.dummy(0, 1)).to_numpy().tobytes()
