@@ -183,19 +183,26 @@ __global__ void __launch_bounds__(256) inner_warp_kernel(const __grid_constant__
   }
 }
 
-// finishing pass: one warp per row merges the chunk partials (lanes stride over the chunks, then a shuffle tree)
+// finishing pass: one CTA per row; threads stride over the chunk partials, then warp shuffles + shared memory
 template <class T, bool MAGN>
 __global__ void __launch_bounds__(256) inner_finish_kernel(const __grid_constant__ InPlan p) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.nrows; row += (int64_t)gridDim.x * 8) {
-    int64_t oa, ob, oc;
-    in_row_offsets<T>(p, row, oa, ob, oc);
+  __shared__ InAcc<T> sh[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     const InAcc<T> *part = reinterpret_cast<const InAcc<T> *>(p.part) + row * p.nchunks;
     InAcc<T> acc; acc.init();
-    for (int64_t k = lane; k < p.nchunks; k += 32) acc.merge(part[k]);
+    for (int64_t k = threadIdx.x; k < p.nchunks; k += 256) acc.merge(part[k]);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const InAcc<T> o = shfl_down_acc(acc, d); acc.merge(o); }
-    if (lane == 0) in_write<T, MAGN>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+    if (lane == 0) sh[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; k++) acc.merge(sh[k]);
+      int64_t oa, ob, oc;
+      in_row_offsets<T>(p, row, oa, ob, oc);
+      in_write<T, MAGN>(p, reinterpret_cast<T *>(p.c) + oc, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -242,8 +249,7 @@ static int inner_go(InPlan &p, cudaStream_t s, const Err &E) {
     if (g > cap * 4) g = cap * 4;
     inner_warp_kernel<T, MAGN><<<(int)g, 256, 0, s>>>(p);
     if (p.nchunks > 1) {
-      int64_t g2 = (p.nrows + 7) / 8;
-      if (g2 > cap) g2 = cap;
+      int64_t g2 = p.nrows < cap * 4 ? p.nrows : cap * 4;
       inner_finish_kernel<T, MAGN><<<(int)g2, 256, 0, s>>>(p);
       note_launch(name);
     }

@@ -43,6 +43,38 @@ template <class T> struct MmxAcc {
   }
 };
 
+// Lane-local running state for the hot loop: 32-bit indices relative to the chunk start, no "have" branch.
+// The extremes start from the identities (+inf / type max for min, -inf / type min for max) and are replaced
+// on STRICT compares only, so the first occurrence in the lane's (increasing) order is kept.  `ifirst` is the
+// first usable element: when every usable element EQUALS an identity the strict compares never fire and the
+// extreme is that identity at `ifirst`.  About 10 instructions per element.
+template <class T> struct MmxLoc {
+  T mn, mx; int imn, imx, ifirst;
+  __device__ __forceinline__ void init() {
+    if constexpr (tt<T>::is_int) {
+      constexpr T hi = tt<T>::is_uns ? T(~T(0)) : T((typename tt<T>::wide_u(1) << (sizeof(T) * 8 - 1)) - 1);
+      constexpr T lo = tt<T>::is_uns ? T(0) : T(-hi - 1);
+      mn = hi; mx = lo;
+    } else { mn = T(INFINITY); mx = T(-INFINITY); }
+    imn = imx = ifirst = -1;
+  }
+  __device__ __forceinline__ void step(T v, int i, bool usable) {   // selects, not branches
+    const bool f = usable && ifirst < 0;
+    ifirst = f ? i : ifirst;
+    const bool lt = usable && v < mn, gt = usable && v > mx;
+    mn = lt ? v : mn; imn = lt ? i : imn;
+    mx = gt ? v : mx; imx = gt ? i : imx;
+  }
+  __device__ __forceinline__ MmxAcc<T> finish(long long base) const {
+    MmxAcc<T> a;
+    a.have = ifirst >= 0;
+    a.mn = mn; a.mx = mx;
+    a.imn = base + (imn >= 0 ? imn : ifirst);
+    a.imx = base + (imx >= 0 ? imx : ifirst);
+    return a;
+  }
+};
+
 template <class A> __device__ __forceinline__ A mmx_shfl_down(const A &v, int d) {
   A r;
   constexpr int NW = (sizeof(A) + 3) / 4;
@@ -78,24 +110,29 @@ __device__ __forceinline__ void mmx_write(const MmxPlan &p, const int64_t (&oo)[
   }
 }
 
-template <class T>
-__device__ __forceinline__ bool mmx_usable(const MmxPlan &p, T v, T abad) {
-  if (p.badmode && is_bad(v, abad, p.abadnan != 0)) return false;
+// CHK = bad mode with an ordinary (non-NaN) badvalue: the only case that needs a compare against it.  NaNs are
+// never usable, so a NaN badvalue needs no test of its own, and integers have no NaN.
+template <class T, bool CHK>
+__device__ __forceinline__ bool mmx_usable(T v, T abad) {
+  if constexpr (CHK) { if (v == abad) return false; }
   return !t_isnan(v);
 }
 
-template <class T>
-__global__ void __launch_bounds__(256) minmaximum_warp_kernel(const __grid_constant__ MmxPlan p) {
+template <class T, bool CHK>
+__global__ void __launch_bounds__(256, 4) minmaximum_warp_kernel(const __grid_constant__ MmxPlan p) {
   const T abad = from_bits<T>(p.abad);
   const int lane = threadIdx.x & 31;
   const int64_t nwork = p.nrows * p.nchunks;
   for (int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < nwork; w += (int64_t)gridDim.x * 8) {
     const int64_t row = w / p.nchunks, chunk = w - row * p.nchunks;
-    int64_t oa, oo[4];
-    mmx_offsets(p, row, oa, oo);
+    int64_t oa = 0;
+    {   // the four output offsets are decoded after the loop (lane 0 only): 8 fewer live registers in it
+      int64_t r = row;
+      for (int d = 0; d < p.nd; d++) { const int64_t q = (d == p.nd - 1) ? 0 : r / p.dims[d]; oa += (r - q * p.dims[d]) * p.sa[d]; r = q; }
+    }
     const T *pa = reinterpret_cast<const T *>(p.a) + oa;
     const int64_t lo = chunk * p.chunk, hi = (lo + p.chunk < p.n) ? lo + p.chunk : p.n;
-    MmxAcc<T> acc; acc.init();
+    MmxLoc<T> loc; loc.init();
     constexpr int U = 4, VEC = 16 / sizeof(T);
     int64_t n = lo + lane;
     if (p.inc_a == 1 && (((uintptr_t)(pa + lo)) & 15) == 0) {
@@ -111,38 +148,55 @@ __global__ void __launch_bounds__(256) minmaximum_warp_kernel(const __grid_const
           const int64_t j = v0 + u * 32 + lane;
           if (j < nvec) {
 #pragma unroll
-            for (int k = 0; k < VEC; k++) { const T v = ra[u].e[k]; if (mmx_usable(p, v, abad)) acc.take(v, lo + j * VEC + k); }
+            for (int k = 0; k < VEC; k++) { const T v = ra[u].e[k]; loc.step(v, (int)(j * VEC + k), mmx_usable<T, CHK>(v, abad)); }
           }
         }
       }
       n = lo + nvec * VEC + lane;
     }
-    for (; n < hi; n += 32) { const T v = pa[n * p.inc_a]; if (mmx_usable(p, v, abad)) acc.take(v, n); }
+    // strided / unaligned rows and the tail of a vectorised chunk: 4 independent loads in flight per lane
+    for (; n + (U - 1) * 32 < hi; n += U * 32) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = pa[(n + u * 32) * p.inc_a];
+#pragma unroll
+      for (int u = 0; u < U; u++) loc.step(v[u], (int)(n + u * 32 - lo), mmx_usable<T, CHK>(v[u], abad));
+    }
+    for (; n < hi; n += 32) { const T v = pa[n * p.inc_a]; loc.step(v, (int)(n - lo), mmx_usable<T, CHK>(v, abad)); }
+    MmxAcc<T> acc = loc.finish(lo);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const MmxAcc<T> o = mmx_shfl_down(acc, d); acc.merge(o); }
     if (lane == 0) {
-      if (p.nchunks == 1) mmx_write<T>(p, oo, acc);
+      if (p.nchunks == 1) { int64_t oo[4]; mmx_offsets(p, row, oa, oo); mmx_write<T>(p, oo, acc); }
       else reinterpret_cast<MmxAcc<T> *>(p.part)[w] = acc;
     }
   }
 }
 
+// finishing pass: one CTA per row; threads stride over the chunk partials, then warp shuffles + shared memory
 template <class T>
 __global__ void __launch_bounds__(256) minmaximum_finish_kernel(const __grid_constant__ MmxPlan p) {
-  const int lane = threadIdx.x & 31;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < p.nrows; row += (int64_t)gridDim.x * 8) {
-    int64_t oa, oo[4];
-    mmx_offsets(p, row, oa, oo);
+  __shared__ MmxAcc<T> sh[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int64_t row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     const MmxAcc<T> *part = reinterpret_cast<const MmxAcc<T> *>(p.part) + row * p.nchunks;
     MmxAcc<T> acc; acc.init();
-    for (int64_t k = lane; k < p.nchunks; k += 32) acc.merge(part[k]);
+    for (int64_t k = threadIdx.x; k < p.nchunks; k += 256) acc.merge(part[k]);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const MmxAcc<T> o = mmx_shfl_down(acc, d); acc.merge(o); }
-    if (lane == 0) mmx_write<T>(p, oo, acc);
+    if (lane == 0) sh[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; k++) acc.merge(sh[k]);
+      int64_t oa, oo[4];
+      mmx_offsets(p, row, oa, oo);
+      mmx_write<T>(p, oo, acc);
+    }
+    __syncthreads();
   }
 }
 
-template <class T>
+template <class T, bool CHK>
 __global__ void __launch_bounds__(256) minmaximum_thread_kernel(const __grid_constant__ MmxPlan p) {
   const T abad = from_bits<T>(p.abad);
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (int64_t)gridDim.x * blockDim.x) {
@@ -150,7 +204,7 @@ __global__ void __launch_bounds__(256) minmaximum_thread_kernel(const __grid_con
     mmx_offsets(p, row, oa, oo);
     const T *pa = reinterpret_cast<const T *>(p.a) + oa;
     MmxAcc<T> acc; acc.init();
-    for (int64_t n = 0; n < p.n; n++) { const T v = pa[n * p.inc_a]; if (mmx_usable(p, v, abad)) acc.take(v, n); }
+    for (int64_t n = 0; n < p.n; n++) { const T v = pa[n * p.inc_a]; if (mmx_usable<T, CHK>(v, abad)) acc.take(v, n); }
     mmx_write<T>(p, oo, acc);
   }
 }
@@ -159,12 +213,14 @@ template <class T>
 static int mmx_go(MmxPlan &p, cudaStream_t s, const Err &E) {
   const int64_t cap = (int64_t)sm_count() * 8;
   const bool per_thread = p.n < 64 && p.nrows >= 1024;
+  const bool chk = p.badmode && !p.abadnan;
   if (!per_thread) {
     int64_t want = cap * 8 / (p.nrows > 0 ? p.nrows : 1);
     if (want < 1) want = 1;
     int64_t chunk = (p.n + want - 1) / want;
     chunk = (chunk + 1023) / 1024 * 1024;
     if (chunk < 1024) chunk = 1024;
+    if (chunk > (1ll << 30)) chunk = 1ll << 30;      // lane-local indices are 32-bit offsets into the chunk
     p.chunk = chunk;
     p.nchunks = p.n > 0 ? (p.n + chunk - 1) / chunk : 1;
   }
@@ -178,14 +234,15 @@ static int mmx_go(MmxPlan &p, cudaStream_t s, const Err &E) {
   if (per_thread) {
     int64_t g = (p.nrows + 255) / 256;
     if (g > cap) g = cap;
-    minmaximum_thread_kernel<T><<<(int)g, 256, 0, s>>>(p);
+    if (chk) minmaximum_thread_kernel<T, true><<<(int)g, 256, 0, s>>>(p);
+    else minmaximum_thread_kernel<T, false><<<(int)g, 256, 0, s>>>(p);
   } else {
     int64_t g = (p.nrows * p.nchunks + 7) / 8;
     if (g > cap * 4) g = cap * 4;
-    minmaximum_warp_kernel<T><<<(int)g, 256, 0, s>>>(p);
+    if (chk) minmaximum_warp_kernel<T, true><<<(int)g, 256, 0, s>>>(p);
+    else minmaximum_warp_kernel<T, false><<<(int)g, 256, 0, s>>>(p);
     if (p.nchunks > 1) {
-      int64_t g2 = (p.nrows + 7) / 8;
-      if (g2 > cap) g2 = cap;
+      int64_t g2 = p.nrows < cap * 4 ? p.nrows : cap * 4;
       minmaximum_finish_kernel<T><<<(int)g2, 256, 0, s>>>(p);
       note_launch("minmaximum");
     }

@@ -180,12 +180,14 @@ def main():
         row("next inner of two float[2^28] (dot product)", lambda: P.run_op("inner", [px, py_], [o0]), 8 * n)
         row("next cumusumover float[2^28] (one row, 3-pass chunked scan)", lambda: P.run_op("cumusumover", [py_], [of]), 8 * n)
         mm = [P.PDL.empty(T.F, [], eng), P.PDL.empty(T.F, [], eng), P.PDL.empty(T.IND, [], eng), P.PDL.empty(T.IND, [], eng)]
-        row("next minmaximum float[2^28] (minmax of a flat ndarray)", lambda: P.run_op("minmaximum", [py_], mm), 4 * n)
+        # minmaximum ends in a flag read-back + stream sync (float rows may be all-NaN), so host-side descriptor
+        # preparation is not hidden behind the kernel: time the prepared descriptor (one C-ABI call)
+        row("next minmaximum float[2^28] (minmax of a flat ndarray; prepared)", P.prepare_op("minmaximum", [py_], mm), 4 * n)
         row("next magnover float[2^28]", lambda: P.run_op("magnover", [py_], [o0]), 4 * n)
         x2 = wrap(eng, x, T.F, [16384, n // 16384])
         mm2 = [P.PDL.empty(T.F, [n // 16384], eng), P.PDL.empty(T.F, [n // 16384], eng),
                P.PDL.empty(T.IND, [n // 16384], eng), P.PDL.empty(T.IND, [n // 16384], eng)]
-        row("next minmaximum float[16384,16384] (per row)", lambda: P.run_op("minmaximum", [x2], mm2), 4 * n)
+        row("next minmaximum float[16384,16384] (per row; prepared)", P.prepare_op("minmaximum", [x2], mm2), 4 * n)
         o2 = wrap(eng, torch.empty(n, dtype=torch.float32, device=dev), T.F, [16384, n // 16384])
         row("next cumusumover float[16384,16384] (warp per row)", lambda: P.run_op("cumusumover", [x2], [o2]), 8 * n)
         del x, m, px, pm, of, ol, od, py_, x2, o2
