@@ -1,4 +1,4 @@
-// reduce_bits.cu — andover orover zcover xorover (all types), lib/PDL/Ufunc.pd:143-187.  Output type == input type.
+// reduce_bitwise.cu — bandover borover bxorover (integer types), lib/PDL/Ufunc.pd:143-187.
 #include "reduce.cuh"
 namespace pdlb200 {
 #define BT_INT(KIND, NAME) \
@@ -13,12 +13,11 @@ namespace pdlb200 {
 #define BT_FLT(KIND, NAME) \
   case PDLB200_F:   return rd_launch_typed<RBits<float,  KIND>, float,  float>(t, NAME, E); \
   case PDLB200_D:   return rd_launch_typed<RBits<double, KIND>, double, double>(t, NAME, E);
-int reduce_logic_family(const pdlb200_trans *t, const Err &E) {
+int reduce_bitwise_family(const pdlb200_trans *t, const Err &E) {
   switch (t->op) {
-    case PDLB200_OP_ANDOVER:  switch (t->datatype) { BT_INT(0, "reduce_andover") BT_FLT(0, "reduce_andover") default: break; } break;
-    case PDLB200_OP_OROVER:   switch (t->datatype) { BT_INT(1, "reduce_orover")  BT_FLT(1, "reduce_orover")  default: break; } break;
-    case PDLB200_OP_ZCOVER:   switch (t->datatype) { BT_INT(2, "reduce_zcover")  BT_FLT(2, "reduce_zcover")  default: break; } break;
-    case PDLB200_OP_XOROVER:  switch (t->datatype) { BT_INT(3, "reduce_xorover") BT_FLT(3, "reduce_xorover") default: break; } break;
+    case PDLB200_OP_BANDOVER: switch (t->datatype) { BT_INT(4, "reduce_bandover") default: break; } break;
+    case PDLB200_OP_BOROVER:  switch (t->datatype) { BT_INT(5, "reduce_borover")  default: break; } break;
+    case PDLB200_OP_BXOROVER: switch (t->datatype) { BT_INT(6, "reduce_bxorover") default: break; } break;
     default: break;
   }
   return E.fail(PDLB200_EUNSUPPORTED, "%s: type %d is not on the device path", pdlb200_op_name(t->op), t->datatype);

@@ -1,4 +1,4 @@
-// reduce_minmax.cu — minimum maximum (lib/PDL/Ufunc.pd:446-475).
+// reduce_minmax_ind.cu — minimum_ind maximum_ind (lib/PDL/Ufunc.pd:477-500).
 #include "reduce.cuh"
 namespace pdlb200 {
 #define MM_CASES(ISMAX, WANT, NAME) \
@@ -18,10 +18,10 @@ static int mm(const pdlb200_trans *t, const char *name, const Err &E) {
   else if constexpr (tt<T>::is_int) return rd_launch_typed<RMinMaxInt<T, ISMAX>, T, T>(t, name, E);
   else return rd_launch_typed<RMinMax<T, T, ISMAX, false>, T, T>(t, name, E);
 }
-int reduce_minmax_family(const pdlb200_trans *t, const Err &E) {
+int reduce_minmax_ind_family(const pdlb200_trans *t, const Err &E) {
   switch (t->op) {
-    case PDLB200_OP_MINIMUM:     switch (t->datatype) { MM_CASES(false, false, "reduce_minimum")     default: break; } break;
-    case PDLB200_OP_MAXIMUM:     switch (t->datatype) { MM_CASES(true,  false, "reduce_maximum")     default: break; } break;
+    case PDLB200_OP_MINIMUM_IND: switch (t->datatype) { MM_CASES(false, true,  "reduce_minimum_ind") default: break; } break;
+    case PDLB200_OP_MAXIMUM_IND: switch (t->datatype) { MM_CASES(true,  true,  "reduce_maximum_ind") default: break; } break;
     default: break;
   }
   return E.fail(PDLB200_EUNSUPPORTED, "%s: type %d is not on the device path", pdlb200_op_name(t->op), t->datatype);
