@@ -6,12 +6,13 @@ mirror of the reference's interface for that path.  There is no CPU fallback."""
 from . import types
 from .types import SB, B, S, US, L, UL, IND, ULL, LL, F, D
 from .engine import CudaEngine, Engine, PDLError, default_engine, set_default_engine
-from .core import PDL, pdl, zeroes, ones, sequence, null
+from .core import PDL, pdl, null
 from .trans import run_op, prepare_op, Prepared, run_biop, run_ufunc, as_pdl, convert_type, SPECS
 from . import ops, ufunc, primitive, bad, basic
+from .basic import zeroes, ones, sequence, xvals, yvals, zvals, axisvals   # device-side constructors (no host build + upload)
 from .primitive import matmult, inner, outer
 
 __all__ = ["PDL", "pdl", "zeroes", "ones", "sequence", "null", "PDLError", "CudaEngine", "Engine",
            "default_engine", "set_default_engine", "run_op", "prepare_op", "Prepared", "run_biop", "run_ufunc", "as_pdl",
            "convert_type", "SPECS", "ops", "ufunc", "primitive", "bad", "basic", "matmult", "inner", "outer", "types",
-           "SB", "B", "S", "US", "L", "UL", "IND", "ULL", "LL", "F", "D"]
+           "xvals", "yvals", "zvals", "axisvals", "SB", "B", "S", "US", "L", "UL", "IND", "ULL", "LL", "F", "D"]

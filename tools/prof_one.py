@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE op of the bench workload a few times (for `ncu --set full -k regex:...`).
-Usage: python tools/prof_one.py {sumover|average|minimum|plus|mult_cfg3|matmult} [reps]"""
+Usage: python tools/prof_one.py {sumover|average|minimum|plus|mult_cfg3|matmult|setbadif|inner|minmaximum|cumusumover|sequence} [reps]"""
 import sys
 from pathlib import Path
 
@@ -42,6 +42,25 @@ elif op == "matmult":
     n = 4096
     A, B, Cc = (torch.rand((n, n), dtype=torch.float64, device=dev) for _ in range(3))
     f = P.prepare_op("matmult", [wrap(A, T.D, [n, n]), wrap(B, T.D, [n, n])], [wrap(Cc, T.D, [n, n])])
+elif op in ("setbadif", "inner", "minmaximum", "cumusumover", "sequence"):
+    n = 2 ** 28
+    x = torch.randint(-8, 9, (n,), device=dev).float()
+    px = wrap(x, T.F, [n])
+    of = P.PDL.empty(T.F, [n], eng)
+    if op == "setbadif":
+        m = (torch.rand(n, device=dev) < 0.1).int()
+        f = P.prepare_op("setbadif", [px, wrap(m, T.L, [n])], [of])
+    elif op == "inner":
+        y = torch.randint(-8, 9, (n,), device=dev).float()
+        f = P.prepare_op("inner", [px, wrap(y, T.F, [n])], [P.PDL.empty(T.F, [], eng)])
+    elif op == "minmaximum":
+        x2 = wrap(x, T.F, [16384, n // 16384])
+        f = P.prepare_op("minmaximum", [x2], [P.PDL.empty(T.F, [n // 16384], eng), P.PDL.empty(T.F, [n // 16384], eng),
+                                              P.PDL.empty(T.IND, [n // 16384], eng), P.PDL.empty(T.IND, [n // 16384], eng)])
+    elif op == "cumusumover":
+        f = P.prepare_op("cumusumover", [wrap(x, T.F, [16384, n // 16384])], [wrap(torch.empty_like(x), T.F, [16384, n // 16384])])
+    else:
+        f = P.prepare_op("axisvalues", [of], [of])
 else:
     raise SystemExit(f"unknown op {op}")
 for _ in range(reps):
