@@ -71,6 +71,38 @@ template <class T> __device__ __forceinline__ T nan_of() {
 
 constexpr int64_t RD_NOIDX = 0x7fffffffffffffffll;
 
+// ---- SIMD-within-a-register helpers for 8/16-bit integer rows ---------------------------------------
+// At 1-2 bytes per element a per-element loop body is issue-bound long before HBM is (5.5 issue slots per
+// byte element at 6.5 TB/s), so sums of small integers work on 32-bit words: BAD lanes are found with the
+// exact zero-lane test on (w ^ badword), cleared, and the word is summed by one dp4a / dp2a.
+template <class T> __device__ __forceinline__ uint32_t swar_splat(T v) {
+  if constexpr (sizeof(T) == 1) return 0x01010101u * (uint32_t)(uint8_t)v; else return 0x00010001u * (uint32_t)(uint16_t)v;
+}
+// all-ones in every lane of w that equals the lane of badw; nbad += number of such lanes
+template <class T> __device__ __forceinline__ uint32_t swar_eq_mask(uint32_t w, uint32_t badw, int32_t &nbad) {
+  const uint32_t x = w ^ badw;
+  if constexpr (sizeof(T) == 1) {
+    const uint32_t hi = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // 0x80 in each zero byte, exact
+    nbad += __popc(hi);
+    return (hi >> 7) * 0xffu;
+  } else {
+    const uint32_t hi = ~(((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u;
+    nbad += __popc(hi);
+    return (hi >> 15) * 0xffffu;
+  }
+}
+// acc + sum of the lanes of w (lanes read as T), wrapping in 32 bits
+template <class T> __device__ __forceinline__ int32_t swar_sum(uint32_t w, int32_t acc) {
+  if constexpr (sizeof(T) == 1) {
+    if constexpr (tt<T>::is_uns) return (int32_t)__dp4a(w, 0x01010101u, (uint32_t)acc); else return __dp4a((int)w, 0x01010101, acc);
+  } else {
+    if constexpr (tt<T>::is_uns) return (int32_t)__dp2a_lo(w, 0x00000101u, (uint32_t)acc); else return __dp2a_lo((int)w, 0x00000101, acc);
+  }
+}
+// reducers opt in with `static constexpr bool kPack` + `lpush_pack<BADK>(Loc &, const Pack<T> &, T abad)`
+template <class R, class = void> struct rd_kpack { static constexpr bool value = false; };
+template <class R> struct rd_kpack<R, std::void_t<decltype(R::kPack)>> { static constexpr bool value = R::kPack; };
+
 // ---- reducers -------------------------------------------------------------------
 // Loc: linit(), lpush(loc, value, rel) with rel = element index - chunk start (int32, increasing
 // per thread); lift(loc, lo) -> Acc.  Acc: init(), merge(l, r) [commutative+associative],
@@ -85,6 +117,21 @@ template <class T, class O> struct RSum {
   struct Acc { O s; int32_t any; int32_t pad; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.any = 0; return x; }
   static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.any = 1; }
+  // 8/16-bit integers into a 32-bit sum: a whole 16-byte image at a time (see swar_* above)
+  static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2 && std::is_same<O, int32_t>::value;
+  template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
+    const uint32_t badw = swar_splat<T>(abad);
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+    int32_t nbad = 0, s = (int32_t)x.s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t g = w[i];
+      if constexpr (BADK == 1) g &= ~swar_eq_mask<T>(g, badw, nbad);
+      s = swar_sum<T>(g, s);
+    }
+    x.s = (O)s;
+    x.any |= (nbad != (int32_t)(16 / sizeof(T)));
+  }
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.s = l.s; x.any = l.any; x.pad = 0; return x; }
   static __device__ __forceinline__ Acc init() { Acc x; x.s = O(0); x.any = 0; x.pad = 0; return x; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = wrap_add<O>(l.s, r.s); x.any = l.any | r.any; x.pad = 0; return x; }
@@ -130,6 +177,20 @@ template <class T, class O> struct RAvg {
   struct Acc { O s; int64_t cnt; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.cnt = 0; return x; }
   static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.cnt++; }
+  static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2 && std::is_same<O, int32_t>::value;
+  template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
+    const uint32_t badw = swar_splat<T>(abad);
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+    int32_t nbad = 0, s = (int32_t)x.s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t g = w[i];
+      if constexpr (BADK == 1) g &= ~swar_eq_mask<T>(g, badw, nbad);
+      s = swar_sum<T>(g, s);
+    }
+    x.s = (O)s;
+    x.cnt += (int32_t)(16 / sizeof(T)) - nbad;
+  }
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.s = l.s; x.cnt = l.cnt; return x; }
   static __device__ __forceinline__ Acc init() { Acc x; x.s = O(0); x.cnt = 0; return x; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = wrap_add<O>(l.s, r.s); x.cnt = l.cnt + r.cnt; return x; }
@@ -345,16 +406,22 @@ __device__ __forceinline__ void rd_row_k(typename R::Loc &loc, const T *row, int
       for (int u = 0; u < R::kUnroll; u++) r[u].q = vp[j + u * width];
 #pragma unroll
       for (int u = 0; u < R::kUnroll; u++) {
-        const int32_t e0 = head + (j + u * width) * VEC;
+        if constexpr (rd_kpack<R>::value) R::template lpush_pack<BADK>(loc, r[u], abad);
+        else {
+          const int32_t e0 = head + (j + u * width) * VEC;
 #pragma unroll
-        for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r[u].e[k], e0 + k, abad);
+          for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r[u].e[k], e0 + k, abad);
+        }
       }
     }
     for (; j < nv; j += width) {
       Pack<T> r; r.q = vp[j];
-      const int32_t e0 = head + j * VEC;
+      if constexpr (rd_kpack<R>::value) R::template lpush_pack<BADK>(loc, r, abad);
+      else {
+        const int32_t e0 = head + j * VEC;
 #pragma unroll
-      for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r.e[k], e0 + k, abad);
+        for (int k = 0; k < VEC; k++) rd_push<R, T, BADK>(loc, r.e[k], e0 + k, abad);
+      }
     }
     for (int32_t i = head + nv * VEC + lane; i < len; i += width) rd_push<R, T, BADK>(loc, base[i], i, abad);
   } else {
