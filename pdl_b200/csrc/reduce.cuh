@@ -293,22 +293,54 @@ template <class T, bool ISMAX> struct RMinMaxInt {
   static constexpr bool kPrefix = false;
   static constexpr bool kRescan = false;
   static constexpr int kUnroll = 4;
-  struct Loc { T cur; int32_t any; };
+  // 8/16-bit types: `pk` holds 4 (2) independent running extremes, one per lane of a 32-bit word, updated by
+  // one packed min/max per word (VIMNMX.x16x2; a few LOP3/PRMT for bytes); BAD lanes are first overwritten with
+  // the identity.  lift() folds the lanes into `cur`.
+  static constexpr bool kPack = sizeof(T) <= 2;
+  struct Loc { T cur; int32_t any; uint32_t pk; };
   struct Acc { T cur; int32_t any; int32_t pad; int32_t pad2; };
   static __device__ __forceinline__ T identity() {
     if constexpr (tt<T>::is_uns) return ISMAX ? T(0) : T(~T(0));
     else { using U = typename std::make_unsigned<T>::type; const T mx = (T)(U(~U(0)) >> 1); return ISMAX ? (T)(-mx - 1) : mx; }
   }
-  static __device__ __forceinline__ Loc linit() { Loc x; x.cur = identity(); x.any = 0; return x; }
-  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) {
-    x.cur = ISMAX ? (v > x.cur ? v : x.cur) : (v < x.cur ? v : x.cur);
-    x.any = 1;
+  static __device__ __forceinline__ T pick(T a, T b) { return ISMAX ? (b > a ? b : a) : (b < a ? b : a); }
+  static __device__ __forceinline__ uint32_t pick_packed(uint32_t a, uint32_t b) {
+    if constexpr (sizeof(T) == 1) {
+      if constexpr (tt<T>::is_uns) return ISMAX ? __vmaxu4(a, b) : __vminu4(a, b); else return ISMAX ? __vmaxs4(a, b) : __vmins4(a, b);
+    } else {
+      if constexpr (tt<T>::is_uns) return ISMAX ? __vmaxu2(a, b) : __vminu2(a, b); else return ISMAX ? __vmaxs2(a, b) : __vmins2(a, b);
+    }
   }
-  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { Acc x; x.cur = l.cur; x.any = l.any; x.pad = 0; x.pad2 = 0; return x; }
+  static __device__ __forceinline__ Loc linit() {
+    Loc x; x.cur = identity(); x.any = 0; x.pk = 0;
+    if constexpr (kPack) x.pk = swar_splat<T>(identity());
+    return x;
+  }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.cur = pick(x.cur, v); x.any = 1; }
+  template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
+    const uint32_t badw = swar_splat<T>(abad), identw = swar_splat<T>(identity());
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+    int32_t nbad = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t g = w[i];
+      if constexpr (BADK == 1) { const uint32_t m = swar_eq_mask<T>(g, badw, nbad); g = (g & ~m) | (identw & m); }
+      x.pk = pick_packed(x.pk, g);
+    }
+    x.any |= (nbad != (int32_t)(16 / sizeof(T)));
+  }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) {
+    Acc x; x.cur = l.cur; x.any = l.any; x.pad = 0; x.pad2 = 0;
+    if constexpr (kPack) {
+#pragma unroll
+      for (int k = 0; k < (int)(4 / sizeof(T)); k++) x.cur = pick(x.cur, (T)(l.pk >> (8 * sizeof(T) * k)));
+    }
+    return x;
+  }
   static __device__ __forceinline__ Acc init() { Acc x; x.cur = identity(); x.any = 0; x.pad = 0; x.pad2 = 0; return x; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
     Acc x; x.any = l.any | r.any; x.pad = 0; x.pad2 = 0;
-    x.cur = ISMAX ? (r.cur > l.cur ? r.cur : l.cur) : (r.cur < l.cur ? r.cur : l.cur);
+    x.cur = pick(l.cur, r.cur);
     return x;
   }
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, T *out) {
@@ -342,6 +374,39 @@ template <class T, int KIND> struct RBits {
     else if constexpr (KIND == 4) x.v &= bits(a);
     else if constexpr (KIND == 5) x.v |= bits(a);
     else x.v ^= bits(a);
+  }
+  // 8/16-bit integers: whole 16-byte images at a time.  Bitwise kinds fold the four words (BAD lanes first set to
+  // the kind's identity) and then the lanes; logical kinds only need "is any good lane (non)zero" per word.
+  static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2;
+  template <int BADK> static __device__ __forceinline__ void lpush_pack(Acc &x, const Pack<T> &r, T abad) {
+    constexpr uint32_t LANE = sizeof(T) == 1 ? 0xffu : 0xffffu;
+    const uint32_t badw = swar_splat<T>(abad);
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+    int32_t nbad = 0, nzero = 0;
+    uint32_t fold = (KIND == 4) ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t m = 0;
+      if constexpr (BADK == 1) m = swar_eq_mask<T>(w[i], badw, nbad);
+      if constexpr (KIND == 4) fold &= (w[i] | m);
+      else if constexpr (KIND == 5) fold |= (w[i] & ~m);
+      else if constexpr (KIND == 6) fold ^= (w[i] & ~m);
+      else if constexpr (KIND == 1 || KIND == 2) fold |= (w[i] & ~m);            // any good lane non-zero?
+      else {                                                                       // KIND 0 / 3: count the good zero lanes
+        int32_t nz_all = 0;
+        const uint32_t z = swar_eq_mask<T>(w[i], 0u, nz_all);
+        if constexpr (BADK == 1) nzero += __popc(z & ~m) / (int)(8 * sizeof(T)); else nzero += nz_all;
+      }
+    }
+    const int32_t ngood = (int32_t)(16 / sizeof(T)) - nbad;
+    x.any |= (ngood != 0);
+    if constexpr (KIND == 4) { fold &= fold >> 16; if constexpr (sizeof(T) == 1) fold &= fold >> 8; x.v &= (fold | ~LANE); }
+    else if constexpr (KIND == 5) { fold |= fold >> 16; if constexpr (sizeof(T) == 1) fold |= fold >> 8; x.v |= (fold & LANE); }
+    else if constexpr (KIND == 6) { fold ^= fold >> 16; if constexpr (sizeof(T) == 1) fold ^= fold >> 8; x.v ^= (fold & LANE); }
+    else if constexpr (KIND == 1) x.v |= U(fold != 0);
+    else if constexpr (KIND == 2) x.v &= U(fold == 0);
+    else if constexpr (KIND == 0) x.v &= U(nzero == 0);
+    else x.v ^= U((ngood - nzero) & 1);
   }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
     Acc x; x.any = l.any | r.any;
