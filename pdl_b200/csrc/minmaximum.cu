@@ -45,32 +45,32 @@ template <class T> struct MmxAcc {
 
 // Lane-local running state for the hot loop: 32-bit indices relative to the chunk start, no "have" branch.
 // The extremes start from the identities (+inf / type max for min, -inf / type min for max) and are replaced
-// on STRICT compares only, so the first occurrence in the lane's (increasing) order is kept.  `ifirst` is the
-// first usable element: when every usable element EQUALS an identity the strict compares never fire and the
-// extreme is that identity at `ifirst`.  About 10 instructions per element.
+// on STRICT compares only, so the first occurrence in the lane's (increasing) order is kept.  A usable element
+// always fires at least one of the two compares (it cannot equal both identities), so "saw a usable element"
+// is imn >= 0 || imx >= 0; if only one side fired, every usable element equals the other side's identity and
+// that extreme sits at the first usable element, which is where the side that did fire recorded its first hit.
+// About 8 ALU instructions per element (the kernel is ALU-pipe bound, not DRAM bound: 4 bytes per element).
 template <class T> struct MmxLoc {
-  T mn, mx; int imn, imx, ifirst;
+  T mn, mx; int imn, imx;
   __device__ __forceinline__ void init() {
     if constexpr (tt<T>::is_int) {
       constexpr T hi = tt<T>::is_uns ? T(~T(0)) : T((typename tt<T>::wide_u(1) << (sizeof(T) * 8 - 1)) - 1);
       constexpr T lo = tt<T>::is_uns ? T(0) : T(-hi - 1);
       mn = hi; mx = lo;
     } else { mn = T(INFINITY); mx = T(-INFINITY); }
-    imn = imx = ifirst = -1;
+    imn = imx = -1;
   }
   __device__ __forceinline__ void step(T v, int i, bool usable) {   // selects, not branches
-    const bool f = usable && ifirst < 0;
-    ifirst = f ? i : ifirst;
     const bool lt = usable && v < mn, gt = usable && v > mx;
     mn = lt ? v : mn; imn = lt ? i : imn;
     mx = gt ? v : mx; imx = gt ? i : imx;
   }
   __device__ __forceinline__ MmxAcc<T> finish(long long base) const {
     MmxAcc<T> a;
-    a.have = ifirst >= 0;
+    a.have = (imn >= 0) || (imx >= 0);
     a.mn = mn; a.mx = mx;
-    a.imn = base + (imn >= 0 ? imn : ifirst);
-    a.imx = base + (imx >= 0 ? imx : ifirst);
+    a.imn = base + (imn >= 0 ? imn : imx);
+    a.imx = base + (imx >= 0 ? imx : imn);
     return a;
   }
 };
