@@ -461,3 +461,24 @@ def test_outer(engines, t):
     # same numbers as the operator on dummy dims (what the reference's docs say outer is)
     (g1, _), (g2, _) = both(engines, a[0], t), both(engines, b, t)
     assert P.outer(g1, g2).to_numpy().tobytes() == (g1.dummy(1, 1) * g2.dummy(0, 1)).to_numpy().tobytes()
+
+
+@pytest.mark.parametrize("t", [T.SB, T.B, T.S, T.US], ids=lambda t: T.NAMES[t])
+def test_small_int_divide_sqrt_exhaustive(engines, t):
+    """8-bit divide runs on one approximate float division and 8/16-bit sqrt on the float square root:
+    check EVERY operand pair / value against the oracle's integer division and double sqrt."""
+    dt = T.NP_DTYPE[t]
+    info = np.iinfo(dt)
+    vals = np.arange(info.min, info.max + 1, dtype=np.int64)
+    if T.SIZE[t] == 1:
+        a = np.repeat(vals, vals.size).astype(dt)
+        b = np.tile(vals, vals.size).astype(dt)
+        keep = b != 0
+        if t == T.SB:
+            keep &= ~((a == -128) & (b == -1))          # INT_MIN / -1 kills the reference (SIGFPE)
+        a, b = a[keep], b[keep]
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"divide-exhaustive-{T.NAMES[t]}", P.run_biop("divide", ga, gb), P.run_biop("divide", oa, ob))
+    v = vals[vals >= 0].astype(dt)
+    (gv, ov) = both(engines, v, t)
+    assert_same(f"sqrt-exhaustive-{T.NAMES[t]}", P.run_ufunc("sqrt", gv), P.run_ufunc("sqrt", ov))
