@@ -144,3 +144,41 @@ def test_long_row_scan_chunked(cuda_engine):
     want = torch.cumsum(torch.where(bad, torch.zeros_like(y), y).view(2, n2).double(), 1).float()
     want[bad.view(2, n2)] = float(out.badvalue)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("case", ["float-2rows-bad", "double-prod", "int64-sum", "int32-3rows-tail"])
+def test_lookback_scan_variants(cuda_engine, case):
+    """The single-pass look-back scan (rows >= 64 tiles of 64 KB, unit-stride, 16-byte aligned): BAD elements,
+    several rows, products, 64-bit accumulators, rows ending inside a vector — against torch's cumsum/cumprod
+    on inputs whose partial results are exactly representable."""
+    g = torch.Generator(device="cuda").manual_seed(23)
+    if case == "float-2rows-bad":
+        n = 2**22 + 8                                   # rows stay 16-byte aligned
+        y = torch.randint(-8, 9, (2 * n,), device="cuda", generator=g).float()
+        bad = torch.rand(2 * n, device="cuda", generator=g) < 0.01
+        y[bad] = -9999.0
+        py = wrap(cuda_engine, y, T.F, [n, 2]).set_badvalue(-9999.0).set_badflag(True)
+        out = ufunc.cumusumover(py)
+        assert cuda_engine.last_kernel() == "scan_cumusumover" and out.badflag
+        want = torch.cumsum(torch.where(bad, torch.zeros_like(y), y).view(2, n).double(), 1).float()
+        want[bad.view(2, n)] = float(out.badvalue)
+        assert torch.equal(as_torch(out, torch.float32).view(2, n), want)
+    elif case == "double-prod":
+        n = 2**21
+        # +-1 and a few +-2: the running product stays a power of two, exact in double
+        y = torch.where(torch.rand(n, device="cuda", generator=g) < 0.5, -1.0, 1.0).double()
+        y[torch.randint(0, n, (40,), device="cuda", generator=g)] = 2.0
+        out = ufunc.cumuprodover(wrap(cuda_engine, y, T.D, [n]))
+        assert torch.equal(as_torch(out, torch.float64), torch.cumprod(y, 0))
+    elif case == "int64-sum":
+        n = 2**21 + 2
+        y = torch.randint(-2**40, 2**40, (n,), device="cuda", generator=g)
+        out = ufunc.cumusumover(wrap(cuda_engine, y, T.LL, [n]))
+        assert torch.equal(as_torch(out, torch.int64), torch.cumsum(y, 0))
+    else:
+        n = 2**22 + 4                                   # int32 rows: 4-element alignment, last tile is partial
+        y = torch.randint(-1000, 1000, (3 * n,), device="cuda", generator=g, dtype=torch.int32)
+        out = ufunc.cumusumover(wrap(cuda_engine, y, T.L, [n, 3]))
+        got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (3 * n,), "typestr": "<i4",
+                              "data": (out.store.ptr, False), "version": 3}})(), device="cuda").view(3, n)
+        assert torch.equal(got, torch.cumsum(y.view(3, n).long(), 1).int())
