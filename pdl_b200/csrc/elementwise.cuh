@@ -15,6 +15,7 @@
 // dims) are gathered element-wise into the same register image, so vaffine views
 // are read in place and never materialised.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -321,7 +322,13 @@ int ew_launch_typed(const pdlb200_trans *t, bool state_checked_bad, const char *
   constexpr int VEC = ew_vec<TI, TO, TB>();
   constexpr int TU = 4;                                    // units per thread per tile
   constexpr int64_t TILE = (int64_t)EW_THREADS * TU * VEC;
-  if (p.nd == 1 || p.dims[0] >= TILE / 2) {
+  // Small contiguous problems (fewer than ~16 tiles per SM, e.g. cfg1's 2048x2048 doubles = 14 per SM) run the
+  // grid-stride kernel on exactly one resident wave of CTAs: every thread gets the same number of units (+-1), so
+  // there is no partial last wave of tiles.  Measured on cfg1: 17.3 us against 17.9 us (a 4-unit variant of the
+  // grid-stride kernel was no faster).  PDLB200_EW_FLAT=<tiles per SM> moves the threshold, 0 disables it.
+  static const int flat_mode = getenv("PDLB200_EW_FLAT") ? atoi(getenv("PDLB200_EW_FLAT")) : 16;
+  const bool small_flat = flat_mode > 0 && p.nd == 1 && p.dims[0] < (int64_t)flat_mode * TILE * sm_count();
+  if (!small_flat && (p.nd == 1 || p.dims[0] >= TILE / 2)) {
     // tile kernel: re-purpose vpr/n_units as tiles-per-row / number of work items.  A work item is
     // `grp` consecutive tiles of one row: 1 for small problems (keeps every SM busy), up to 8 for
     // big ones (amortises the per-item index decode).
