@@ -173,4 +173,62 @@ def pmax_ind(local: PDL, comm: Comm) -> PDL:
     return _collapse(local, comm, "max_ind", local.datatype)
 
 
-__all__ = ["split_dim", "shard", "Comm", "psum", "pavg", "pmin", "pmax", "pmin_ind", "pmax_ind"]
+def pminmax(local: PDL, comm: Comm):
+    """minmax() of a sharded ndarray (lib/PDL/Ufunc.pd:738 over :563-613): ONE local pass (minmaximum on the
+    flat block) instead of separate min and max reductions, then 48-byte records all-gathered and merged in
+    rank order.  BAD and NaN elements are skipped; no usable element anywhere -> (BAD, BAD).
+    Returns two 0-dim ndarrays."""
+    flat = local.flat()
+    rec = np.zeros(6, dtype=np.uint64)           # have, min bits, min index, max bits, max index, pad
+    sizes = comm.all_gather_bytes(np.array([local.nelem], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
+    offset = int(sizes[:comm.rank].sum())
+    if flat.nelem:
+        cmin, cmax, imin, imax = ufunc.minmaximum(flat)
+        if not (cmin.badflag and cmin.bad_mask().any()):     # the flag alone may just be propagated from the input
+            rec[:] = [1, T.value_bits(cmin.datatype, cmin.sclr()), int(imin.sclr()) + offset,
+                      T.value_bits(cmax.datatype, cmax.sclr()), int(imax.sclr()) + offset, 0]
+    recs = comm.all_gather_bytes(rec.view(np.uint8)).view(np.uint64).reshape(comm.world, 6)
+    t = local.datatype
+    best = None
+    for r in recs:
+        if not r[0]:
+            continue
+        mn, mx = T.bits_value(t, int(r[1])), T.bits_value(t, int(r[3]))
+        if best is None:
+            best = [mn, int(r[2]), mx, int(r[4])]
+            continue
+        if mn < best[0] or (mn == best[0] and r[2] < best[1]):
+            best[0], best[1] = mn, int(r[2])
+        if mx > best[2] or (mx == best[2] and r[4] < best[3]):
+            best[2], best[3] = mx, int(r[4])
+    outs = []
+    for v in ((best[0], best[2]) if best else (T.DEFAULT_BAD[t], T.DEFAULT_BAD[t])):
+        o = PDL.from_numpy(np.array(v, dtype=T.NP_DTYPE[t]), t, local.engine)
+        o.badflag = best is None or local.badflag
+        outs.append(o)
+    return tuple(outs)
+
+
+def pinner(a_local: PDL, b_local: PDL, comm: Comm) -> PDL:
+    """inner() of two ndarrays sharded the same way over their (flattened) n (lib/PDL/Primitive.pd:48-70): the
+    local dot product on the device, then the per-rank partials added in rank order; a BAD element on any rank
+    makes the result BAD."""
+    from .primitive import inner
+    part = inner(a_local.flat(), b_local.flat())
+    t = part.datatype
+    bad = 1 if part.badflag and part.bad_mask().any() else 0
+    rec = np.array([bad, T.value_bits(t, part.sclr()) if not bad else 0], dtype=np.uint64)
+    recs = comm.all_gather_bytes(rec.view(np.uint8)).view(np.uint64).reshape(comm.world, 2)
+    dt = T.NP_DTYPE[t]
+    anybad = bool(recs[:, 0].any())
+    with np.errstate(over="ignore"):
+        tot = dt.type(0)
+        for r in recs:
+            if not r[0]:
+                tot = dt.type(tot + T.bits_value(t, int(r[1])))
+    out = PDL.from_numpy(np.array(T.DEFAULT_BAD[t] if anybad else tot, dtype=dt), t, a_local.engine)
+    out.badflag = anybad or a_local.badflag or b_local.badflag
+    return out
+
+
+__all__ = ["split_dim", "shard", "Comm", "psum", "pavg", "pmin", "pmax", "pmin_ind", "pmax_ind", "pminmax", "pinner"]

@@ -61,6 +61,23 @@ def _worker(rank, world, port, q):
                 res[f"{name}-{T.NAMES[t]}"] = g.tobytes().hex()
             gi = parallel.pmax_ind(mine, comm).sclr()
             assert gi == ufunc.maximum_ind(whole.flat()).sclr(), ("max_ind", T.NAMES[t])
+            # minmax in one local pass (minmaximum) + merge; inner of two identically sharded ndarrays
+            gmn, gmx = parallel.pminmax(mine, comm)
+            emn, emx, _, _ = ufunc.minmaximum(whole.flat())
+            assert gmn.to_numpy().tobytes() == emn.to_numpy().tobytes(), ("minmax-min", T.NAMES[t])
+            assert gmx.to_numpy().tobytes() == emx.to_numpy().tobytes(), ("minmax-max", T.NAMES[t])
+            other = np.abs(rng.integers(0, 3, size=full.shape)).astype(T.NP_DTYPE[t])
+            clean = np.where(full == bad, 1, full).astype(T.NP_DTYPE[t])
+            if t in (T.F, T.D):
+                clean[3, 7] = 2
+            if t == T.B:
+                clean, other = clean % 2, other % 2          # keep the dot product inside the 8-bit result type
+            wa, wb = P.PDL.from_numpy(clean, t, eng), P.PDL.from_numpy(other, t, eng)
+            gin = parallel.pinner(parallel.shard(wa, rank, world), parallel.shard(wb, rank, world), comm)
+            ein = P.inner(wa.flat(), wb.flat())
+            assert gin.to_numpy().tobytes() == ein.to_numpy().tobytes(), ("inner", T.NAMES[t], gin.to_numpy(), ein.to_numpy())
+            gbad = parallel.pinner(mine, parallel.shard(wb, rank, world), comm)     # BAD elements on some rank -> BAD
+            assert gbad.badflag and gbad.bad_mask().all(), ("inner-bad", T.NAMES[t])
         # all-BAD and empty blocks
         allbad = P.PDL.from_numpy(np.full((4, 6), T.DEFAULT_BAD[T.F], dtype=np.float32), T.F, eng).set_badflag(True)
         r = parallel.psum(parallel.shard(allbad, rank, world), comm)
