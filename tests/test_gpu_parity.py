@@ -482,3 +482,44 @@ def test_small_int_divide_sqrt_exhaustive(engines, t):
     v = vals[vals >= 0].astype(dt)
     (gv, ov) = both(engines, v, t)
     assert_same(f"sqrt-exhaustive-{T.NAMES[t]}", P.run_ufunc("sqrt", gv), P.run_ufunc("sqrt", ov))
+
+
+def test_cabi_error_returns_on_device(cuda_engine):
+    """Malformed descriptors come back as error codes + messages through the C-ABI, never as a crash or a
+    silently wrong launch: missing `anybad` for the ops that need it, wrong fixed parameter types, a type
+    outside the device matrix, an op id that does not exist."""
+    import ctypes as C
+    from pdl_b200 import _abi, trans
+    lib, err = cuda_engine.lib, C.create_string_buffer(512)
+    a = P.PDL.from_numpy(np.arange(8, dtype=np.float32), T.F, cuda_engine)
+    o = P.PDL.empty(T.F, [8], cuda_engine)
+
+    def desc(name, pdls, named=None, ttype=T.F):
+        spec = trans.SPECS[name]
+        bc = trans._broadcast(pdls, [len(p.realdims) for p in spec.pars], [False] * len(pdls), name)
+        tr = trans._build_trans(spec, ttype, pdls, bc, named or {}, False)
+        return tr
+
+    # setnantobad / minmaximum without anybad
+    tr = desc("setnantobad", [a, o]); tr.anybad = None
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"anybad" in err.value
+    s = [P.PDL.empty(T.F, [], cuda_engine), P.PDL.empty(T.F, [], cuda_engine),
+         P.PDL.empty(T.IND, [], cuda_engine), P.PDL.empty(T.IND, [], cuda_engine)]
+    tr = desc("minmaximum", [a] + s, {"ind": [8], "rinc": [1]}); tr.anybad = None
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"anybad" in err.value
+    # setbadif with a float mask, isbad with a float output
+    tr = desc("setbadif", [a, a, o])
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"mask" in err.value
+    tr = desc("isbad", [a, o])
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"int" in err.value
+    # magnover of an integer type, an unknown op, a type outside the matrix
+    li = P.PDL.from_numpy(np.arange(8, dtype=np.int32), T.L, cuda_engine)
+    tr = desc("magnover", [li, P.PDL.empty(T.L, [], cuda_engine)], {"ind": [8], "rinc": [1]}, ttype=T.L)
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EUNSUPPORTED
+    tr = desc("plus", [a, a, o]); tr.op = 49
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"unknown op" in err.value
+    tr = desc("plus", [a, a, o]); tr.datatype = 12
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EUNSUPPORTED and b"no device representation" in err.value
+    # and the engine turns them into PDLError for the host mirror
+    with pytest.raises(P.PDLError):
+        cuda_engine.readdata(tr)
