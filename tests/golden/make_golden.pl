@@ -465,3 +465,46 @@ for my $t (@TYPES) {
 }
 add_case("outer-empty", [[mk('double',[0],'small')],[mk('double',[3],'small')]], {kind=>'outer'});
 flush_cases('outer.json');
+
+# ---------------------------------------------------------------- edge shapes for the rows either side of the path
+{
+  my $m3 = mk('double',[6,4,3],'small');
+  add_case("edge-setbadif-3d-broadcast-mask", [[$m3],[pdl(long,[[0,1,0,0,1,0]])]], {kind=>'badop', op=>'setbadif'});
+  add_case("edge-setbadif-col-mask", [[mk('short',[5,4],'small')],[pdl(long,[1,0,0,1])->dummy(0,1)]], {kind=>'badop', op=>'setbadif'});
+  add_case("edge-setbadtoval-reversed-view", [[with_bad(mk('long',[12],'small'), 2, 7), [['slice','-1:0']]],{scalar=>-5, is_int=>1}], {kind=>'badop', op=>'setbadtoval'});
+  add_case("edge-isbad-0dim", [[with_bad(mk('float',[1],'small'), 0), [['slice','(0)']]]], {kind=>'badop', op=>'isbad'});
+  add_case("edge-isgood-empty", [[mk('double',[0,3],'small')]], {kind=>'badop', op=>'isgood'});
+  add_case("edge-copybad-broadcast", [[mk('float',[7,3],'small')],[with_bad(mk('float',[7],'small'), 1, 5)]], {kind=>'badop', op=>'copybad'});
+  add_case("edge-badmask-nan-badvalue", [[do { my $d = mk('double',[22],'special')->copy; $d->badflag(1); $d->badvalue($NAN); $d }],{scalar=>0, is_int=>1}], {kind=>'badop', op=>'badmask'});
+  add_case("edge-setvaltobad-negative-on-unsigned", [[mk('byte',[9],'mixed')],{scalar=>-1, is_int=>1}], {kind=>'badop', op=>'setvaltobad'});
+  add_case("edge-setbadtoval-frac-on-int", [[with_bad(mk('long',[9],'small'), 1, 4)],{scalar=>2.75}], {kind=>'badop', op=>'setbadtoval'});
+  add_case("edge-inner-reversed", [[mk('double',[40],'small'), [['slice','-1:0']]],[mk('double',[40],'small')]], {kind=>'inner'}, 0);
+  add_case("edge-inner-stride3-x-dummy", [[mk('float',[30,4],'small'), [['slice','0:-1:3,:']]],[mk('float',[10],'small')]], {kind=>'inner'}, 0);
+  add_case("edge-inner-xchg", [[mk('long',[6,9],'small'), [['xchg',0,1]]],[mk('long',[9],'small')]], {kind=>'inner'});
+  add_case("edge-inner-scalar-b", [[mk('double',[5,3],'small')],{scalar=>2.5}], {kind=>'inner'}, 0);
+  add_case("edge-outer-dummy", [[mk('long',[4],'small'), [['dummy',1,3]]],[mk('long',[5],'small')]], {kind=>'outer'});
+  add_case("edge-outer-1x1", [[mk('double',[1],'small')],[mk('double',[1],'small')]], {kind=>'outer'});
+  add_case("edge-minmaximum-1elem", [[mk('float',[1,5],'mixed')]], {kind=>'minmaximum'});
+  add_case("edge-minmaximum-xchg", [[mk('short',[7,40],'small'), [['xchg',0,1]]]], {kind=>'minmaximum'});
+  add_case("edge-minmaximum-inf", [[pdl(double, [[$INF,-$INF,1],[$INF,$INF,$INF],[-$INF,-$INF,-$INF],[$NAN,$INF,$NAN]])]], {kind=>'minmaximum'});
+  add_case("edge-minmaximum-intmax", [[pdl(long, [[2147483647,2147483647],[-2147483648,-2147483648],[2147483647,-2147483648]])]], {kind=>'minmaximum'});
+  add_case("edge-minmaximum-bytes-ident", [[pdl(byte, [[255,255,255],[0,0,0],[0,255,0]])]], {kind=>'minmaximum'});
+  add_case("edge-sequence-1", [], {kind=>'sequence', type=>'double', dims=>[1]});
+  add_case("edge-sequence-byte-wrap", [], {kind=>'sequence', type=>'byte', dims=>[300]});
+  add_case("edge-sequence-float-big", [], {kind=>'sequence', type=>'float', dims=>[5,7,3,2]});
+  add_case("edge-zvals-2d", [[mk('double',[4,3],'small')]], {kind=>'axis', op=>'zvals'});
+  add_case("edge-yvals-reversed-view", [[mk('float',[6,5],'small'), [['slice',':,-1:0']]]], {kind=>'axis', op=>'yvals'});
+  for my $t (qw(byte sbyte short ushort)) {
+    my $row = mk($t,[700,3],'mixed');                     # rows long enough for the packed 16-byte paths, odd alignment via slice
+    my $b = with_bad($row, 5, 699, 700, 1399, (map { 1400 + $_ } 0..699));
+    for my $op (qw(sumover average minimum maximum orover andover bandover borover bxorover zcover xorover)) {
+      add_case("edge-packed-$op-$t", [[$row, [['slice','3:-2,:']]]], {kind=>'reduce', op=>$op});
+      add_case("edge-packed-bad-$op-$t", [[$b, [['slice','1:-1,:']]]], {kind=>'reduce', op=>$op});
+    }
+    add_case("edge-packed-minmaximum-$t", [[$b]], {kind=>'minmaximum'});
+  }
+  add_case("edge-magnover-xchg", [[mk('double',[5,60],'small'), [['xchg',0,1]]]], {kind=>'reduce', op=>'magnover'}, 1);
+  add_case("edge-cumusumover-reversed", [[mk('long',[50,2],'small'), [['slice','-1:0,:']]]], {kind=>'reduce', op=>'cumusumover'});
+  add_case("edge-cumuprodover-bad-first", [[with_bad(mk('double',[9,2],'small'), 0, 9)]], {kind=>'reduce', op=>'cumuprodover'}, 0);
+}
+flush_cases('edge.json');
