@@ -182,3 +182,29 @@ def test_lookback_scan_variants(cuda_engine, case):
         got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (3 * n,), "typestr": "<i4",
                               "data": (out.store.ptr, False), "version": 3}})(), device="cuda").view(3, n)
         assert torch.equal(got, torch.cumsum(y.view(3, n).long(), 1).int())
+
+
+def test_elementwise_beyond_2_pow_32_elements(cuda_engine):
+    """More than 2^32 elements in one elementwise launch (64-bit unit/item arithmetic in the walkers): sbyte
+    plus over 2^32 + 37 elements, checked through slices at the start, across the 2^32 boundary and at the end,
+    and the device-side sequence (axisvalues) of the same length."""
+    n = 2**32 + 37
+    if torch.cuda.mem_get_info()[0] < 4 * n:
+        pytest.skip("needs ~17 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randint(-50, 50, (n,), device="cuda", dtype=torch.int8, generator=g)
+    b = torch.randint(-50, 50, (n,), device="cuda", dtype=torch.int8, generator=g)
+    out = wrap(cuda_engine, a, T.SB, [n]) + wrap(cuda_engine, b, T.SB, [n])
+    assert out.dims == [n]
+    got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "|i1",
+                          "data": (out.store.ptr, False), "version": 3}})(), device="cuda")
+    for lo, hi in ((0, 10**6), (2**32 - 10**6, 2**32 + 37), (2**31 - 1000, 2**31 + 1000)):
+        assert torch.equal(got[lo:hi], a[lo:hi] + b[lo:hi]), (lo, hi)
+    del a, b, got, out
+    from pdl_b200 import basic
+    s = basic.sequence(T.B, n, engine=cuda_engine)          # byte: values wrap mod 256 exactly like the reference's (T)n
+    sv = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "|u1",
+                         "data": (s.store.ptr, False), "version": 3}})(), device="cuda")
+    for lo in (0, 2**32 - 500, n - 300):
+        want = (torch.arange(lo, lo + 300, device="cuda", dtype=torch.int64) % 256).to(torch.uint8)
+        assert torch.equal(sv[lo:lo + 300], want), lo
