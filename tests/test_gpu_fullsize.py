@@ -208,3 +208,23 @@ def test_elementwise_beyond_2_pow_32_elements(cuda_engine):
     for lo in (0, 2**32 - 500, n - 300):
         want = (torch.arange(lo, lo + 300, device="cuda", dtype=torch.int64) % 256).to(torch.uint8)
         assert torch.equal(sv[lo:lo + 300], want), lo
+
+
+def test_scan_row_longer_than_2_pow_31(cuda_engine):
+    """One row of 2^31 + 11 elements through the chunked scan (64-bit chunk arithmetic; sbyte in, long out)."""
+    n = 2**31 + 11
+    if torch.cuda.mem_get_info()[0] < 24 * 2**30:
+        pytest.skip("needs ~24 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(6)
+    a = torch.randint(-1, 2, (n,), device="cuda", dtype=torch.int8, generator=g)
+    out = ufunc.cumusumover(wrap(cuda_engine, a, T.SB, [n]))
+    assert out.type == "long" and out.dims == [n]
+    got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "<i4",
+                          "data": (out.store.ptr, False), "version": 3}})(), device="cuda")
+    # check in blocks of 2^28 against torch, carrying the running total
+    carry, blk = 0, 2**28
+    for lo in range(0, n, blk):
+        hi = min(lo + blk, n)
+        want = torch.cumsum(a[lo:hi].to(torch.int32), 0, dtype=torch.int32) + carry
+        assert torch.equal(got[lo:hi], want), lo
+        carry = int(want[-1].item())
