@@ -16,3 +16,21 @@ __all__ = ["PDL", "pdl", "zeroes", "ones", "sequence", "null", "PDLError", "Cuda
            "default_engine", "set_default_engine", "run_op", "prepare_op", "Prepared", "run_biop", "run_ufunc", "as_pdl",
            "convert_type", "SPECS", "ops", "ufunc", "primitive", "bad", "basic", "matmult", "inner", "outer", "types",
            "xvals", "yvals", "zvals", "axisvals", "SB", "B", "S", "US", "L", "UL", "IND", "ULL", "LL", "F", "D"]
+
+
+def _attach_methods() -> None:
+    """In PDL every op is also a method (`$x->sumover`, `$x->setbadif($m)`, `$x->xvals`, `$x->inner($y)`):
+    give the mirror the same spelling.  Names that the class already defines (views, copy, ...) are kept."""
+    table = {}
+    for mod, names in ((ufunc, ufunc.__all__), (bad, bad.__all__), (primitive, primitive.__all__),
+                       (basic, ("xvals", "yvals", "zvals", "axisvals")), (ops, getattr(ops, "__all__", ()))):
+        for n in names:
+            f = getattr(mod, n, None)
+            if callable(f):
+                table[n] = f
+    for n, f in table.items():
+        if not hasattr(PDL, n):
+            setattr(PDL, n, (lambda fn: lambda self, *a, **k: fn(self, *a, **k))(f))
+
+
+_attach_methods()

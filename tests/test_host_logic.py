@@ -99,3 +99,16 @@ def test_badflag_propagation(oracle_engine):
     d = P.PDL.from_numpy(np.array([T.DEFAULT_BAD[T.L], 5, 6], dtype=np.int32), T.L, e)
     r = d + b
     assert r.to_numpy()[0] == np.int32(T.DEFAULT_BAD[T.L]) + np.int32(1)      # computed (wraps), not forced BAD
+
+
+def test_ops_are_also_methods(oracle_engine):
+    """`$x->sumover`, `$x->setbadif($m)->isbad`, `$x->inner($y)`, `$x->minmax`, `$x->yvals`: the op surface as methods."""
+    e = oracle_engine
+    x = P.sequence(T.F, 5, 3, engine=e)
+    assert x.sumover().to_numpy().tolist() == [10.0, 35.0, 60.0]
+    assert x.minmax() == (0.0, 14.0)
+    m = P.PDL.from_numpy(np.array([0, 1, 0, 0, 1], dtype=np.int32), T.L, e)
+    assert x.setbadif(m).isbad().sumover().to_numpy().tolist() == [2, 2, 2]
+    assert x.inner(x).to_numpy().tolist() == [30.0, 255.0, 730.0]
+    assert x.yvals().to_numpy()[2].tolist() == [2.0] * 5
+    assert x.setbadif(m).setbadtoval(-1).minimum().to_numpy().tolist() == [-1.0, -1.0, -1.0]
