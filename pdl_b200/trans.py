@@ -256,13 +256,16 @@ class Prepared:
     The cached-descriptor fast path for repeated shapes (SURVEY.md §7 "launch-latency floor"):
     type selection, broadcast merging and output creation were done once by prepare_op()."""
 
-    __slots__ = ("engine", "trans", "outputs", "_keep")
+    __slots__ = ("engine", "trans", "outputs", "_keep", "_flagged")
 
-    def __init__(self, engine, trans, outputs, keep):
-        self.engine, self.trans, self.outputs, self._keep = engine, trans, outputs, keep
+    def __init__(self, engine, trans, outputs, keep, flagged=False):
+        self.engine, self.trans, self.outputs, self._keep, self._flagged = engine, trans, outputs, keep, flagged
 
     def __call__(self):
         self.engine.readdata(self.trans)
+        if self._flagged and self.trans._anybad.value:     # `if (flag) $PDLSTATESETBAD(...)` of the op's Code
+            for o in self.outputs:
+                o.badflag = True
         return self.outputs
 
 
@@ -307,10 +310,10 @@ def _real_inc(p: PDL, j: int) -> int:
     return 0 if (p.ndims <= j or p.dims[j] <= 1) else p.dimincs[j]
 
 
-def prepare_op(name: str, inputs: list, outputs: list | None = None) -> Prepared:
+def prepare_op(name: str, inputs: list, outputs: list | None = None, param: float = 0.0) -> Prepared:
     """Like run_op, but returns a Prepared instead of launching.  Only for calls that need no
     type conversion of inputs or outputs (a single readdata)."""
-    return run_op(name, inputs, outputs, _prepare=True)
+    return run_op(name, inputs, outputs, _prepare=True, param=param)
 
 
 def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False, param: float = 0.0):
@@ -422,7 +425,14 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     if _prepare:
         if temps:
             raise PDLError(f"PDL::{name}: prepare_op needs outputs already in the operation's type")
-        return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder)
+        if name in _STATE_SETBAD:
+            for o in placeholder[len(ins):]:
+                o.badflag = True
+        elif name in _STATE_SETGOOD:
+            for o in placeholder[len(ins):]:
+                o.badflag = False
+        return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder,
+                        flagged=name in _STATE_IFFLAG)
     flag = _launch(spec, transtype, placeholder, bc, named, bval)
     if name in _STATE_SETBAD or (name in _STATE_IFFLAG and flag):
         for o in placeholder[len(ins):]:

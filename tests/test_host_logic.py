@@ -112,3 +112,29 @@ def test_ops_are_also_methods(oracle_engine):
     assert x.inner(x).to_numpy().tolist() == [30.0, 255.0, 730.0]
     assert x.yvals().to_numpy()[2].tolist() == [2.0] * 5
     assert x.setbadif(m).setbadtoval(-1).minimum().to_numpy().tolist() == [-1.0, -1.0, -1.0]
+
+
+def test_prepared_ops_apply_output_state_rules(oracle_engine):
+    """prepare_op + call must leave the same badflags as run_op: data-dependent for setnantobad / minmaximum,
+    unconditional for setbadif / setbadtoval."""
+    e = oracle_engine
+    x = P.PDL.from_numpy(np.array([1.0, np.nan, 3.0], dtype=np.float32), T.F, e)
+    out = P.PDL.empty(T.F, [3], e)
+    P.prepare_op("setnantobad", [x], [out])()
+    assert out.badflag and out.bad_mask().tolist() == [False, True, False]
+    clean = P.PDL.from_numpy(np.array([1.0, 2.0, 3.0], dtype=np.float32), T.F, e)
+    out2 = P.PDL.empty(T.F, [3], e)
+    P.prepare_op("setnantobad", [clean], [out2])()
+    assert not out2.badflag
+    allnan = P.PDL.from_numpy(np.full((2, 3), np.nan, dtype=np.float32), T.F, e)
+    outs = [P.PDL.empty(T.F, [2], e), P.PDL.empty(T.F, [2], e), P.PDL.empty(T.IND, [2], e), P.PDL.empty(T.IND, [2], e)]
+    P.prepare_op("minmaximum", [allnan], outs)()
+    assert all(o.badflag for o in outs)
+    m = P.PDL.from_numpy(np.array([0, 1, 0], dtype=np.int32), T.L, e)
+    out3 = P.PDL.empty(T.F, [3], e)
+    P.prepare_op("setbadif", [clean, m], [out3])()
+    assert out3.badflag
+    b = clean.copy().set_badflag(True)
+    out4 = P.PDL.empty(T.F, [3], e)
+    P.prepare_op("setbadtoval", [b], [out4])()
+    assert not out4.badflag
