@@ -121,3 +121,67 @@ def test_primitive_matmult_t_fiducials(e):
     C = P.matmult(A, basic.sequence(T.D, 2, 3, engine=e))
     B.setbadtoval(C.inplace(), 6)
     assert vals(C) == [[6, 6], [2, 3], [4, 5]]                              # t/primitive-matmult.t:93-99
+
+
+def bad_at(p):
+    """(values with BAD as None) for comparing against the reference's 'BAD' literals."""
+    a, m = p.to_numpy().reshape(-1).tolist(), p.bad_mask().reshape(-1).tolist() if p.badflag else [False] * p.nelem
+    return [None if b else v for v, b in zip(a, m)]
+
+
+def test_bad_t_propagation_and_queries(e):
+    BAD = 255
+    x = d(e, [1, 2, 3], T.B).set_badflag(True)
+    y = d(e, [1, BAD, 3], T.B).set_badflag(True)
+    assert bad_at(x + y) == [2, None, 6]                                    # t/bad.t:111
+    c = y.convert(T.F)
+    assert c.type == "float" and bad_at(c) == [1.0, None, 3.0]              # t/bad.t:115
+    assert ufunc.sum(c).sclr() == 4 and ufunc.sum(c).type == "float"        # t/bad.t:116
+    x = d(e, [1, 2, BAD, BAD, 5, 6, BAD, 8, 9], T.B).set_badflag(True)
+    assert B.isbad(x).type == "long" and vals(B.isbad(x)) == [0, 0, 1, 1, 0, 0, 1, 0, 0]    # t/bad.t:119
+    assert vals(B.isgood(x)) == [1, 1, 0, 0, 1, 1, 0, 1, 1]                 # t/bad.t:120
+    assert ufunc.nbadover(x.flat()).sclr() == 3 and ufunc.ngoodover(x.flat()).sclr() == 6   # t/bad.t:121-122
+    nan = float("nan")
+    assert vals(B.isnan(d(e, [1, 2, nan, nan, 5, 6, nan, 8, 9]))) == [0, 0, 1, 1, 0, 0, 1, 0, 0]   # t/bad.t:125
+    x = d(e, [[BAD, BAD], [BAD, 0], [0, 0]], T.B).set_badflag(True)
+    assert ufunc.nbadover(x).type == "indx" and vals(ufunc.nbadover(x)) == [2, 1, 0]        # t/bad.t:128
+    assert vals(ufunc.ngoodover(x)) == [0, 1, 2]                            # t/bad.t:129
+    assert bad_at(d(e, [1, 2, BAD, 4], T.B).set_badflag(True) << 2) == [4, 8, None, 16]     # t/bad.t:250
+
+
+def test_bad_t_setbad_family(e):
+    data = [42, 47, 98, 13, 22, 96, 74, 41, 79, 76, 96, 3, 32, 76, 25, 59, 5, 96, 32, 6]
+    want = [42, 47, 98, 20, 22, 96, 74, 41, 79, 76, 96, 20, 32, 76, 25, 59, 20, 96, 32, 20]
+    mask = [0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1]
+    x = d(e, data)
+    y = B.setbadif(x, x < 20)
+    assert y.badflag
+    assert vals(B.setbadtoval(y, 20)) == want and y.badflag                 # t/bad.t:175-177
+    B.setbadtoval(y.inplace(), 20)
+    assert vals(y) == want and not y.badflag                                # t/bad.t:180-183
+    y = B.setbadif(x, x < 20)
+    assert vals(B.isbad(B.copybad(x, y))) == mask                           # t/bad.t:186-190
+    x2 = d(e, data)
+    B.copybad(x2.inplace(), y)
+    assert vals(B.isbad(x2)) == mask                                        # t/bad.t:192-196
+    nan, inf = float("nan"), float("inf")
+    x = d(e, [0, 1, -9, 3, 4]).set_badvalue(-9.0).set_badflag(True)
+    B.badmask(x.inplace(), 0)
+    assert vals(x) == [0, 1, 0, 3, 4] and not x.badflag                     # t/bad.t:314-316
+    x = basic.sequence(T.D, 10, engine=e) % 4
+    B.setvaltobad(x.inplace(), 1)
+    assert bad_at(x) == [0, None, 2, 3, 0, None, 2, 3, 0, None]             # t/bad.t:319-321
+    B.setbadtonan(x.inplace())
+    got = vals(x)
+    assert [v != v for v in got] == [False, True, False, False] * 2 + [False, True] and not x.badflag   # t/bad.t:323-324
+    assert bad_at(B.setvaltobad(d(e, [1, 2, 3, 4], T.F), 2)) == [1, None, 3, 4]             # t/bad.t:327
+    assert bad_at(B.setvaltobad(d(e, [1, 2, 3, 4], T.D), 2)) == [1, None, 3, 4]             # t/bad.t:328
+    i2b = d(e, [0, inf, nan])
+    B.setinftobad(i2b.inplace())
+    r = bad_at(i2b)
+    assert r[0] == 0 and r[1] is None and r[2] != r[2]                      # t/bad.t:330-332
+    xc = d(e, [0, inf, 2, 3, 0, nan, 2, 3, 0, nan])
+    B.setnonfinitetobad(xc.inplace())
+    assert bad_at(xc) == [0, None, 2, 3, 0, None, 2, 3, 0, None]            # t/bad.t:334-336
+    B.setnantobad(x.inplace())
+    assert bad_at(x) == [0, None, 2, 3, 0, None, 2, 3, 0, None]             # t/bad.t:343
