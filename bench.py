@@ -10,9 +10,14 @@ One STEP = those three reductions over the whole 4 GiB ndarray (3 x 2^30 element
   roofline  : slowest of the three kernels; achieved = algorithmic bytes / CUDA-event time.
   N > 1     : one process per GPU; the ndarray is partitioned along its outermost broadcast
               dim (rows), every rank reduces its own [16384, 65536] block, no data-path
-              collective -> weak scaling.  `extra.cfg5` additionally times
-              the full-array sum/max of the same resident 2^30-element shard per GPU plus the
-              NCCL allreduce that collapses the sharded dim (BASELINE.json configs[4]).
+              collective -> weak scaling.
+  extra     : the other BASELINE.json configs under the same clock.  `cfg5` (every N): full-array sum
+              and max of a float ndarray of 2^30 elements PER GPU (2^33 at N = 8) sharded along its only
+              dim, through the product's sharded-reduction API (pdl_b200.parallel.pcollapse: device
+              partial records -> ONE ncclAllGather -> device merge), input = SURVEY.md §8(d)'s
+              ({-1,0,+1} counter hash + one planted maximum), verified against exact integer sums;
+              `cfg5_strong`: the same with a fixed 2^30-element ndarray split N ways.  `cfg1`, `cfg3`,
+              `cfg4`, `perl` (N = 1 only): tools/config_legs.py and perl/PDL-B200/bench_ops.pl.
   --impl reference : the UNMODIFIED reference (PDL built into oracle/_ref) on the host cores,
               all threads, on a bounded sample of the same workload.
 """
@@ -31,6 +36,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+REF_ROWS = 4096        # the ONE bounded CPU sample: 4096 of 65536 rows (256 MiB), in cpu_baseline and --impl reference
+REF_WARMUP = 2         # at least this many untimed steps (page-in of the sample) in both places
 N_DIM = 16384          # reduced dim (dim 0), contiguous
 ROWS = 65536           # broadcast dim per GPU
 WORKLOAD = "cfg2: sumover+average+minimum over dim 0 of float[16384,65536], 1% BAD"
@@ -84,6 +91,34 @@ def generate_device(torch, row0: int, rows: int, device):
         vals[bad] = -torch.finfo(torch.float32).max
         out[r:r + rr] = vals.view(rr, N_DIM)
     return out
+
+
+def generate_cfg5(torch, g0: int, count: int, device, plant_at: int = -1, plant_value: float = 3.0):
+    """SURVEY.md §8(d) cfg5 input for global flat indices [g0, g0 + count): x[i] in {-1, 0, +1} from the counter
+    hash (partial sums stay far below 2^24, so float accumulation is exact in any order) and, if `plant_at`
+    falls in the range, one planted maximum.  Returns (float32 tensor, exact int64 sum of it)."""
+    out = torch.empty(count, dtype=torch.float32, device=device)
+    m1 = 0xBF58476D1CE4E5B9 - (1 << 64)
+    m2 = 0x94D049BB133111EB - (1 << 64)
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    total = torch.zeros((), dtype=torch.int64, device=device)
+    step = 1 << 25
+    for r in range(0, count, step):
+        rr = min(step, count - r)
+        z = torch.arange(rr, dtype=torch.int64, device=device) + (g0 + r + SEED)
+        z = (z ^ lsr(z, 30)) * m1
+        z = (z ^ lsr(z, 27)) * m2
+        z = z ^ lsr(z, 31)
+        v = lsr(z, 11) % 3 - 1
+        total += v.sum()
+        out[r:r + rr] = v.to(torch.float32)
+    if g0 <= plant_at < g0 + count:
+        total += int(plant_value) - int(out[plant_at - g0].item())
+        out[plant_at - g0] = plant_value
+    return out, total
 
 
 # ---------------------------------------------------------------------------------------------
@@ -160,15 +195,33 @@ def run_port_sample(rows, steps, warmup):
     return {"ms_per_step": 1000 * tot / steps, "elements_per_sec": 3 * rows * N_DIM * steps / tot}
 
 
+def run_perl_bench():
+    """The reference-facing plugin call under real PDL: perl/PDL-B200/bench_ops.pl times `$x = $y + $c`,
+    a 3-op chain and ->sumover/->average/->minimum through the UNCHANGED operator surface, first on the
+    reference's CPU path, then with the PDL::B200 shim attached (same process, same ndarrays)."""
+    ref = ROOT / "oracle" / "_ref" / "blib"
+    shim = ROOT / "perl" / "PDL-B200" / "blib"
+    if not (shim / "arch" / "auto" / "PDL" / "B200" / "B200.so").exists() or not _have_ref():
+        return {"error": "PDL::B200 shim or oracle/_ref not built"}
+    cmd = ["perl", f"-I{ref / 'lib'}", f"-I{ref / 'arch'}", f"-I{shim / 'lib'}", f"-I{shim / 'arch'}",
+           str(ROOT / "perl" / "PDL-B200" / "bench_ops.pl"), "--reps", "50"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    out["workload"] = "perl: the operator surface under real PDL 2.106, CPU path vs PDL::B200 shim (ms per op, wall clock)"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    rows = 4096  # bounded sample: 4096 of 65536 rows = 256 MiB; reference time scales linearly in rows
+    rows = REF_ROWS  # bounded sample: 4096 of 65536 rows = 256 MiB; reference time scales linearly in rows
     if _have_ref():
-        res = run_reference_sample(rows, args.steps, args.warmup, cores)
+        res = run_reference_sample(rows, args.steps, max(args.warmup, REF_WARMUP), cores)
         kind, threads = "reference", int(res.get("autopthread_actual") or 0) or 1
         detail = f"PDL {res['pdl_version']} autopthread target {cores}, actual {res.get('autopthread_actual')}"
     else:
@@ -358,47 +411,92 @@ def main_ours(args):
     e2e_value = elems_step * e2e_steps / float(t.item())
     e2e_ok = bool(np.array_equal(host_out[0].numpy().view(np.uint32), outs["sumover"].to_numpy().view(np.uint32)))
 
-    # ---- cfg5 extra: full-array sum / max of the resident shard + allreduce over the sharded dim ----
-    flat = a.reshape_view([N_DIM * ROWS])
-    part = torch.zeros(4, dtype=torch.float32, device=device)
-    psum = P.PDL(eng, eng.wrap(part.data_ptr(), 4, part), T.F, [])
-    pmax = P.PDL(eng, eng.wrap(part.data_ptr() + 4, 4, part), T.F, [])
-    psum.badflag = pmax.badflag = True
+    # ---- cfg5 extra: full-array sum + max of a sharded 1-D float ndarray through the product's API ----
+    from pdl_b200 import parallel
 
-    def cfg5():
-        P.run_op("sumover", [flat], [psum])
-        P.run_op("maximum", [flat], [pmax])
+    class _Solo:                     # N = 1: same code path, the "gather" of one rank's records is a device copy
+        rank, world, backend = 0, 1, "nccl"
+        _bufs = {}
+        record_buffers = parallel.Comm.record_buffers
+
+        def all_gather_records(self, engine, lt, gt):
+            gt.copy_(lt)
+
+    comm = parallel.Comm() if dist is not None else _Solo()
+
+    def cfg5_leg(per_gpu: int, label: str):
+        total_n = per_gpu * world
+        g0 = rank * per_gpu
+        plant_at = (total_n * 5) // 7 + 11
+        x, exact = generate_cfg5(torch, g0, per_gpu, device, plant_at, 3.0)
         if dist is not None:
-            dist.all_reduce(part[0:1], op=dist.ReduceOp.SUM)
-            dist.all_reduce(part[1:2], op=dist.ReduceOp.MAX)
+            dist.all_reduce(exact, op=dist.ReduceOp.SUM)         # checker only: exact integer sum of the whole ndarray
+        want_sum = int(exact.item())
+        px = P.PDL(eng, eng.wrap(x.data_ptr(), per_gpu * 4, x), T.F, [per_gpu])
+        res = [None]
 
-    for _ in range(3):
-        cfg5()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        cfg5()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cfg5_ms = float(t.item()) / args.steps
-    cfg5_extra = {"workload": f"cfg5: sum+max of float[2^30] per GPU x {world} GPUs" + (" + NCCL allreduce" if world > 1 else ""),
-                  "ms_per_step": cfg5_ms, "elements_per_sec": 2 * N_DIM * ROWS * world / (cfg5_ms / 1e3),
-                  "gbs_per_gpu": 2 * nbytes_in / cfg5_ms / 1e6, "frac_per_gpu": 2 * nbytes_in / cfg5_ms / 1e6 / peak,
-                  "sum": float(part[0].item()), "max": float(part[1].item())}
+        def step5():
+            res[0] = parallel.pcollapse(px, comm, ("sum", "max"), offset=g0, total=total_n)
+
+        for _ in range(3):
+            step5()
+        barrier()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step5()
+        e1.record()
+        barrier()
+        nl = (eng.launch_count() - l0) // args.steps
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item()) / args.steps
+        got_sum, got_max = res[0][0].to_numpy(), res[0][1].to_numpy()
+        got_ind = int(parallel.pcollapse(px, comm, ("max_ind",), offset=g0, total=total_n)[0].sclr())
+        ok = (abs(want_sum) < 2 ** 24 and got_sum.tobytes() == np.float32(want_sum).tobytes()
+              and got_max.tobytes() == np.float32(3.0).tobytes() and got_ind == plant_at)
+        same = torch.tensor([int(got_sum.view(np.uint32)), int(got_max.view(np.uint32)), got_ind], dtype=torch.int64, device=device)
+        if dist is not None:                                     # identical bits on every rank
+            lo, hi = same.clone(), same.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            ok = ok and bool(torch.equal(lo, hi))
+        del x
+        return {"workload": label, "api": "pdl_b200.parallel.pcollapse(flat, comm, ('sum','max'))",
+                "ms_per_step": ms, "elements_per_sec": 2 * total_n / (ms / 1e3),
+                "gbs_per_gpu": 2 * per_gpu * 4 / ms / 1e6, "frac_per_gpu": 2 * per_gpu * 4 / ms / 1e6 / peak,
+                "launches_per_step": int(nl), "collectives_per_step": 1 if world > 1 else 0,
+                "sum": float(got_sum), "max": float(got_max), "max_ind": got_ind, "verified": bool(ok)}
+
+    cfg5_extra = cfg5_leg(N_DIM * ROWS, f"cfg5: sum+max of float[2^30 x {world}] sharded over {world} GPU(s), weak")
+    cfg5_strong = cfg5_leg(N_DIM * ROWS // world, f"cfg5 strong: sum+max of float[2^30] split over {world} GPU(s)")
+
+    # ---- the other BASELINE configs and the Perl plugin call, N = 1 only ----
+    extra = {"cfg5": cfg5_extra, "cfg5_strong": cfg5_strong}
+    if rank == 0 and world == 1 and not args.no_extra:
+        sys.path.insert(0, str(ROOT / "tools"))
+        import config_legs
+        for name, fn in (("cfg1", lambda: config_legs.cfg1(eng, device, peak)),
+                         ("cfg3", lambda: config_legs.cfg3(eng, device, peak)),
+                         ("cfg4", lambda: config_legs.cfg4(eng, device)),
+                         ("perl", run_perl_bench)):
+            try:
+                extra[name] = fn()
+            except Exception as ex:  # an extra leg never takes the headline down with it
+                extra[name] = {"error": f"{type(ex).__name__}: {ex}"[:400]}
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline on this box's host cores (rank 0, N == 1 only; bounded sample) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rows = 8192
-        sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step, 3 timed steps"
+        rows = REF_ROWS
+        sample = f"{rows} of {ROWS} rows ({rows * N_DIM * 4 >> 20} MiB), 3 ops per step, {args.steps} timed steps"
         try:
             if _have_ref():
-                r1 = run_reference_sample(rows, 3, 1, cores)
+                r1 = run_reference_sample(rows, args.steps, max(args.warmup, REF_WARMUP), cores)
                 r0 = run_reference_sample(rows, 3, 1, 0)
                 cpu_baseline = {"value": r1["elements_per_sec"], "unit": "elements/s",
                                 "cores": int(r1.get("autopthread_actual") or 0) or 1, "kind": "reference",
@@ -432,7 +530,7 @@ def main_ours(args):
         "sustained": {"ms_per_step": sustained_ms, "steps": sustained_steps,
                       "value": elems_step / world / (sustained_ms / 1e3)},
         "verified_vs_oracle": verified,
-        "cpu_baseline": cpu_baseline, "extra": {"cfg5": cfg5_extra},
+        "cpu_baseline": cpu_baseline, "extra": extra,
     }
     print(json.dumps(line))
     return 0
@@ -445,5 +543,6 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg1/cfg3/cfg4/perl legs")
     a = ap.parse_args()
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -34,7 +34,7 @@ extern "C" {
 #define PDLB200_API
 #endif
 
-#define PDLB200_ABI_VERSION 3
+#define PDLB200_ABI_VERSION 4
 
 /* Element types: numeric values are PDL's own pdl_datatypes enum
  * (lib/PDL/Types.pm:27-255, order is significant for promotion).
@@ -98,6 +98,21 @@ enum {
   /* outer, lib/PDL/Primitive.pd:78-96 : a(n); b(m); [o]c(n,m) — c = a*b; ind = {n, m},
    * rinc = {inc_a_n, inc_b_m, inc_c_n, inc_c_m}.  Runs as mult over two extra leading broadcast dims. */
   PDLB200_OP_OUTER = 79,
+  /* Whole-array reductions of an ndarray PARTITIONED across GPUs along its outermost dim (SURVEY.md §8(e);
+   * the reference's own split rule, lib/PDL/Core/pdlbroadcast.c:469-484) collapse the sharded dim in three
+   * steps, all on the device: (1) PART_*: the rank's block reduced to one 32-byte record per row,
+   * a(n); longlong [o]rec(r=4) with rec = {value bits, good count, GLOBAL index, state}; state 0 = no good
+   * element, 1 = value is not NaN, 2 = every good element is NaN (value = the LAST one, Ufunc.pd:455-465).
+   * ind[0] = n, ind[1] = global index of this block's element 0, rinc[0] = inc_a_n, rinc[1] = inc_rec_r.
+   * PART_SUM accumulates in the `int+` type of `datatype` (sumover/average, Ufunc.pd:88-118,413-444),
+   * PART_DSUM in double (dsumover/daverage).  (2) the records of all ranks are gathered (ncclAllGather or
+   * peer stores).  (3) COLL_*: longlong rec(r=4,k); [o]b() merges the k records of a row IN RANK ORDER with
+   * the reference's rules (BAD skipped, all BAD -> BAD, NaN loses to non-NaN, first index wins), so every
+   * rank holds the same bits.  `datatype` = the type of the VALUE in the records (the int+/double type for
+   * SUM/AVG, the input type for MIN/MAX); ind[0] = k, rinc[0] = inc_rec_r, rinc[1] = inc_rec_k. */
+  PDLB200_OP_PART_SUM = 80, PDLB200_OP_PART_DSUM, PDLB200_OP_PART_MIN, PDLB200_OP_PART_MAX,
+  PDLB200_OP_COLL_SUM = 84, PDLB200_OP_COLL_AVG, PDLB200_OP_COLL_MIN, PDLB200_OP_COLL_MAX,
+  PDLB200_OP_COLL_MIN_IND, PDLB200_OP_COLL_MAX_IND,
   PDLB200_OP__END
 };
 

@@ -63,8 +63,11 @@ OPS = {
     "isbad": 63, "isgood": 64, "isnan": 65, "setbadif": 66, "setvaltobad": 67,
     "setnantobad": 68, "setinftobad": 69, "setnonfinitetobad": 70, "setbadtonan": 71,
     "setbadtoval": 72, "badmask": 73, "copybad": 74, "axisvalues": 75, "inner": 76, "minmaximum": 77, "magnover": 78, "outer": 79,
+    # sharded whole-array reductions: per-rank partial records and their rank-ordered merge
+    "part_sum": 80, "part_dsum": 81, "part_min": 82, "part_max": 83,
+    "coll_sum": 84, "coll_avg": 85, "coll_min": 86, "coll_max": 87, "coll_min_ind": 88, "coll_max_ind": 89,
 }
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/pdlb200.h declares (tests check the .so exports them all)
 SYMBOLS = [

@@ -37,13 +37,15 @@ def _default_incs(dims: Sequence[int]) -> list[int]:
 class PDL:
     """Device-resident ndarray.  dims[0] is the fastest-varying dim, as in PDL."""
 
-    __slots__ = ("engine", "store", "datatype", "dims", "dimincs", "offs", "badflag",
-                 "_badvalue", "_inplace", "_null")
+    __slots__ = ("engine", "_store", "datatype", "dims", "dimincs", "offs", "badflag",
+                 "_badvalue", "_inplace", "_null", "_flowing", "_pending")
 
     def __init__(self, engine: Engine, store: Store | None, datatype: int, dims, dimincs=None,
                  offs: int = 0, badflag: bool = False, badvalue=None):
         self.engine = engine
-        self.store = store
+        self._store = store
+        self._pending = None        # (op name, inputs): a deferred transformation whose readdata has not run yet
+        self._flowing = False
         self.datatype = datatype
         self.dims = [int(d) for d in dims]
         self.dimincs = [int(i) for i in (dimincs if dimincs is not None else _default_incs(self.dims))]
@@ -81,6 +83,41 @@ class PDL:
         p = cls(engine or default_engine(), None, T.D, [0])
         p._null = True
         return p
+
+    # ---- dataflow: deferred readdata (lib/PDL/Core/pdlapi.c:781-801,890) ---------------
+    @property
+    def store(self):
+        """The device allocation.  An ndarray produced by an op on a `flowing` parent has none until
+        something needs its data: then the deferred transformation runs (pdl__ensure_trans from
+        make_physical, pdlapi.c:886-905)."""
+        if self._pending is not None:
+            self._materialize()
+        return self._store
+
+    @store.setter
+    def store(self, st):
+        self._store = st
+
+    def flowing(self) -> "PDL":
+        """`$x->flowing`: turn on dataflow for the NEXT operation (PDL_DATAFLOW_F; cleared by
+        make_trans_mutual, pdlapi.c:781-785).  That operation's readdata is deferred until its result is
+        needed — which lets a reduction that is the result's only consumer run fused with it."""
+        v = self._view(self.dims, self.dimincs, self.offs)
+        v._flowing = True
+        return v
+
+    def is_pending(self) -> bool:
+        return self._pending is not None
+
+    def _materialize(self) -> None:
+        name, ins = self._pending
+        self._pending = None
+        n = 1
+        for d in self.dims:
+            n *= d
+        self._store = self.engine.alloc(n * T.SIZE[self.datatype])
+        from .trans import run_op
+        run_op(name, ins, [self])
 
     # ---- introspection ----------------------------------------------------------------
     @property

@@ -99,6 +99,10 @@ static void init_names() {
   N(PDLB200_OP_SETBADTONAN, "setbadtonan") N(PDLB200_OP_SETBADTOVAL, "setbadtoval") N(PDLB200_OP_BADMASK, "badmask")
   N(PDLB200_OP_COPYBAD, "copybad") N(PDLB200_OP_AXISVALUES, "axisvalues") N(PDLB200_OP_INNER, "inner")
   N(PDLB200_OP_MINMAXIMUM, "minmaximum") N(PDLB200_OP_MAGNOVER, "magnover") N(PDLB200_OP_OUTER, "outer")
+  N(PDLB200_OP_PART_SUM, "part_sum") N(PDLB200_OP_PART_DSUM, "part_dsum") N(PDLB200_OP_PART_MIN, "part_min")
+  N(PDLB200_OP_PART_MAX, "part_max") N(PDLB200_OP_COLL_SUM, "coll_sum") N(PDLB200_OP_COLL_AVG, "coll_avg")
+  N(PDLB200_OP_COLL_MIN, "coll_min") N(PDLB200_OP_COLL_MAX, "coll_max") N(PDLB200_OP_COLL_MIN_IND, "coll_min_ind")
+  N(PDLB200_OP_COLL_MAX_IND, "coll_max_ind")
 #undef N
 }
 
@@ -190,6 +194,8 @@ int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
   if (t->op == PDLB200_OP_INNER) return launch_inner(t, E);
   if (t->op == PDLB200_OP_MINMAXIMUM) return launch_minmaximum(t, E);
   if (t->op == PDLB200_OP_MAGNOVER) return launch_magnover(t, E);
+  if (t->op >= PDLB200_OP_PART_SUM && t->op <= PDLB200_OP_PART_MAX) return launch_partial(t, E);
+  if (t->op >= PDLB200_OP_COLL_SUM && t->op <= PDLB200_OP_COLL_MAX_IND) return launch_collapse(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
 }
 int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
@@ -210,6 +216,8 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   if (op >= PDLB200_OP_CUMUSUMOVER && op <= PDLB200_OP_DCUMUPRODOVER) return launch_scan(t, E);
   if (op >= PDLB200_OP_SUMOVER && op <= PDLB200_OP_NGOODOVER) return launch_reduce(t, E);
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);
+  if (op >= PDLB200_OP_PART_SUM && op <= PDLB200_OP_PART_MAX) return launch_partial(t, E);
+  if (op >= PDLB200_OP_COLL_SUM && op <= PDLB200_OP_COLL_MAX_IND) return launch_collapse(t, E);
   return E.fail(PDLB200_EINVAL, "pdlb200: op %d has no launcher", op);
 }
 

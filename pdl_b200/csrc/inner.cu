@@ -70,7 +70,9 @@ template <> struct InAcc<double> {
   }
   __device__ void add(double a, double b) { addv(a * b); }
   __device__ void merge(const InAcc &o) { addv(o.s); c += o.c; bad |= o.bad; }
-  __device__ double result() const { return s + c; }
+  // a non-finite running sum (an inf element, or overflow) leaves NaN in the compensation term (inf - inf): the
+  // reference's long double accumulator just carries the inf/NaN, so does `s`
+  __device__ double result() const { return isfinite(s) ? s + c : s; }
 };
 
 template <class A> __device__ __forceinline__ A shfl_down_acc(const A &v, int d) {
@@ -104,7 +106,7 @@ __device__ __forceinline__ void in_write(const InPlan &p, T *out, const InAcc<T>
     if constexpr (tt<T>::is_int) *out = acc.result();
     else {
       double sum;
-      if constexpr (sizeof(T) == 8) sum = acc.s + acc.c; else sum = acc.s;
+      if constexpr (sizeof(T) == 8) sum = acc.result(); else sum = acc.s;
       *out = sum == 0 ? T(0) : (T)sqrt(sum);
     }
   } else {

@@ -42,7 +42,7 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
 
   int64_t oa = 0, ob = 0, oc = 0;
   {
-    int64_t row = blockIdx.z;
+    int64_t row = p.z0 + blockIdx.z;
     for (int d = 0; d < p.nd; d++) {
       const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
       const int64_t i = row - q * p.dims[d];
@@ -137,13 +137,18 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
 }
 
 template <class T>
-static int mm_launch(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
-  dim3 grid((unsigned)((p.W + MM_BN - 1) / MM_BN), (unsigned)((p.H + MM_BM - 1) / MM_BM), (unsigned)p.nbatch);
+static int mm_launch(const pdlb200_trans *t, const MmPlan &plan, const Err &E) {
   cudaStream_t s = (cudaStream_t)t->stream;
-  if (t->bvalflag) mm_exact_kernel<T, true><<<grid, 256, 0, s>>>(p);
-  else mm_exact_kernel<T, false><<<grid, 256, 0, s>>>(p);
-  note_launch("matmult_exact");
-  PDLB200_CUDA_OK(cudaGetLastError(), E);
+  MmPlan p = plan;
+  // broadcast positions ride on gridDim.z (<= 65535): batches of many small matrices go out in slices
+  for (p.z0 = 0; p.z0 < p.nbatch; p.z0 += MM_MAXZ) {
+    const int64_t nz = (p.nbatch - p.z0 < MM_MAXZ) ? p.nbatch - p.z0 : MM_MAXZ;
+    dim3 grid((unsigned)((p.W + MM_BN - 1) / MM_BN), (unsigned)((p.H + MM_BM - 1) / MM_BM), (unsigned)nz);
+    if (t->bvalflag) mm_exact_kernel<T, true><<<grid, 256, 0, s>>>(p);
+    else mm_exact_kernel<T, false><<<grid, 256, 0, s>>>(p);
+    note_launch("matmult_exact");
+    PDLB200_CUDA_OK(cudaGetLastError(), E);
+  }
   return PDLB200_OK;
 }
 
@@ -160,7 +165,6 @@ int launch_matmult(const pdlb200_trans *t, const Err &E) {
   p.nd = c.nd; p.nbatch = c.total;
   for (int d = 0; d < c.nd; d++) { p.dims[d] = c.dims[d]; p.sa[d] = c.st[0][d]; p.sb[d] = c.st[1][d]; p.sc[d] = c.st[2][d]; }
   if (p.nbatch == 0 || p.H == 0 || p.W == 0) return PDLB200_OK;
-  if (p.nbatch > 65535) return E.fail(PDLB200_EUNSUPPORTED, "matmult: %lld broadcast positions exceed the 65535 grid limit", (long long)p.nbatch);
   const size_t sz = pdlb200_type_size(t->datatype);
   for (int k = 0; k < 3; k++)
     if (!t->pdls[k].data) return E.fail(PDLB200_EINVAL, "matmult: parameter %d got NULL data", k);

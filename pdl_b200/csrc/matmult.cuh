@@ -4,6 +4,8 @@
 
 namespace pdlb200 {
 
+constexpr int64_t MM_MAXZ = 65535;  // gridDim.z limit
+
 struct MmPlan {
   const char *a, *b; char *c;      // bases with offs applied
   int64_t T, H, W;                 // sizes of t, h, w
@@ -11,6 +13,7 @@ struct MmPlan {
   int64_t dims[MAXD];              // collapsed broadcast (batch) dims
   int64_t sa[MAXD], sb[MAXD], sc[MAXD];
   int64_t nbatch;
+  int64_t z0;                      // first broadcast position of this launch (grids are cut at 65535 in z)
   uint64_t abad, bbad, cbad;
   int nd;
   int abadnan, bbadnan, cbadnan;

@@ -64,7 +64,7 @@ mm_dmma_kernel(const __grid_constant__ MmPlan p) {
 
   int64_t oa = 0, ob = 0, oc = 0;
   {
-    int64_t row = blockIdx.z;
+    int64_t row = p.z0 + blockIdx.z;
     for (int d = 0; d < p.nd; d++) {
       const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
       const int64_t i = row - q * p.dims[d];
@@ -267,7 +267,7 @@ mm_dmma_ws_kernel(const __grid_constant__ MmPlan p) {
 
   int64_t oa = 0, ob = 0, oc = 0;
   {
-    int64_t row = blockIdx.z;
+    int64_t row = p.z0 + blockIdx.z;
     for (int d = 0; d < p.nd; d++) {
       const int64_t q = (d == p.nd - 1) ? 0 : row / p.dims[d];
       const int64_t i = row - q * p.dims[d];
@@ -418,7 +418,20 @@ static int dmma_ws_go(const MmPlan &p, dim3 grid, cudaStream_t s, const Err &E) 
   return PDLB200_OK;
 }
 
-int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
+static int launch_matmult_dmma_slice(const pdlb200_trans *t, const MmPlan &p, int64_t nz, const Err &E);
+
+int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &plan, const Err &E) {
+  MmPlan p = plan;
+  for (p.z0 = 0; p.z0 < p.nbatch || p.z0 == 0; p.z0 += MM_MAXZ) {   // gridDim.z <= 65535: slices
+    const int64_t nz = (p.nbatch - p.z0 < MM_MAXZ) ? p.nbatch - p.z0 : MM_MAXZ;
+    const int rc = launch_matmult_dmma_slice(t, p, nz, E);
+    if (rc) return rc;
+    if (p.nbatch <= MM_MAXZ) break;
+  }
+  return PDLB200_OK;
+}
+
+static int launch_matmult_dmma_slice(const pdlb200_trans *t, const MmPlan &p, int64_t nz, const Err &E) {
   // eligibility: unit stride along t in a and along w in b (PDL's default physical layout)
   if (p.T == 0) return PDLB200_EUNSUPPORTED;
   if (!((p.iat == 1 || p.T == 1) && (p.ibw == 1 || p.W == 1))) return PDLB200_EUNSUPPORTED;
@@ -426,7 +439,7 @@ int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
   bool aligned = ((((uintptr_t)p.a) | ((uintptr_t)p.b)) & 15) == 0 && (p.iah % 2 == 0) && (p.ibt % 2 == 0) &&
                  p.iat == 1 && p.ibw == 1;
   for (int d = 0; d < p.nd && aligned; d++) if ((p.sa[d] % 2) || (p.sb[d] % 2)) aligned = false;
-  dim3 grid((unsigned)((p.W + DM_BN - 1) / DM_BN), (unsigned)((p.H + DM_BM - 1) / DM_BM), (unsigned)p.nbatch);
+  dim3 grid((unsigned)((p.W + DM_BN - 1) / DM_BN), (unsigned)((p.H + DM_BM - 1) / DM_BM), (unsigned)nz);
   cudaStream_t s = (cudaStream_t)t->stream;
   const char *sh = getenv("PDLB200_DMMA_SHAPE");
   const int shape = (sh && !strcmp(sh, "884")) ? 0 : 1;

@@ -40,6 +40,7 @@ struct RdPlan {
   int64_t dims[MAXD];
   int64_t sa[MAXD], sb[MAXD];   // broadcast strides of a and b (elements)
   int64_t chunk;                // elements of n per chunk (== n when nchunks == 1); always < 2^31
+  int64_t goff, inc_r;          // PART_* ops: global index of element 0, stride of the record's r dim
   char *partial;                // scratch for nchunks > 1
   uint64_t abad, bbad;
   int nd;

@@ -20,6 +20,7 @@ int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_
   memset(p, 0, sizeof *p);
   p->n = t->ind[0];
   p->inc_n = t->rinc[0];
+  p->goff = t->ind[1]; p->inc_r = t->rinc[1];   // read by the PART_* reducers only (reduce_shard.cu)
   p->nrows = c.total;
   p->nd = c.nd;
   for (int d = 0; d < c.nd; d++) { p->dims[d] = c.dims[d]; p->sa[d] = c.st[0][d]; p->sb[d] = c.st[1][d]; }

@@ -6,9 +6,9 @@ chosen dim, the first `dim % nthr` workers one element more.  Elementwise ops an
 over a non-sharded dim need NO collective — every rank runs the ordinary single-GPU call on
 its block (bench.py does exactly that).  Only a reduction that collapses the sharded dim (the
 whole-array wrappers sum / avg / min / max ..., lib/PDL/Ufunc.pd:618-663) exchanges data:
-each rank reduces its block on the device to ONE partial record, the records are all-gathered
-over NCCL (32 bytes per rank over NVLink/NVSwitch; gloo on CPU for the tests) and every rank
-finishes them in rank order with the reference's own semantics (BAD -> skipped, all BAD -> BAD,
+each rank reduces its block on the device to ONE partial record (PART_* ops), the records are
+all-gathered over NCCL (32 bytes per rank over NVLink/NVSwitch; gloo on CPU for the tests) and every
+rank merges them ON THE DEVICE (COLL_* ops) in rank order with the reference's own semantics (BAD -> skipped, all BAD -> BAD,
 NaN loses to non-NaN, first index wins), so all ranks hold the same bit pattern.
 """
 from __future__ import annotations
@@ -17,7 +17,7 @@ import numpy as np
 
 from . import types as T
 from .core import PDL
-from .engine import PDLError
+from .engine import PDLError, Store
 from . import ufunc
 
 
@@ -51,6 +51,7 @@ class Comm:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+        self._bufs = {}
 
     def all_gather_bytes(self, rec: np.ndarray) -> np.ndarray:
         """rec: uint8[k] on the host -> uint8[world, k], identical on every rank."""
@@ -62,115 +63,132 @@ class Comm:
             self.dist.all_gather(list(out.unbind(0)), t, group=self.group)
         return out.cpu().numpy()
 
+    # ---- device-side record exchange -----------------------------------------------------------
+    def record_buffers(self, engine, nwords: int):
+        """(local, gathered) longlong ndarrays of `nwords` and `world * nwords` elements that
+        torch.distributed can address: device memory under nccl, host memory under gloo.  Cached per size;
+        reuse is safe because every use is ordered on the engine's stream."""
+        key = (id(engine), nwords)
+        if key not in self._bufs:
+            import torch
+            dev = f"cuda:{engine.device}" if self.backend == "nccl" else "cpu"
+            lt = torch.zeros(nwords, dtype=torch.int64, device=dev)
+            gt = torch.zeros(self.world * nwords, dtype=torch.int64, device=dev)
+            mk = (lambda t: engine.wrap(t.data_ptr(), t.numel() * 8, t)) if hasattr(engine, "wrap") else \
+                (lambda t: Store(engine, None, t.data_ptr(), t.numel() * 8, t))
+            self._bufs[key] = (lt, gt, PDL(engine, mk(lt), T.LL, [nwords]), PDL(engine, mk(gt), T.LL, [nwords, self.world]))
+        return self._bufs[key]
 
-_REC = np.dtype([("val", "u8"), ("ngood", "i8"), ("idx", "i8"), ("state", "i8")])
+    def all_gather_records(self, engine, lt, gt) -> None:
+        """ONE collective: every rank's `lt` into `gt` (rank-major), on the engine's stream."""
+        if self.backend == "nccl":
+            import contextlib
+            import torch
+            cm = torch.cuda.stream(torch.cuda.ExternalStream(engine.stream)) if getattr(engine, "stream", None) else contextlib.nullcontext()
+            with cm:
+                self.dist.all_gather_into_tensor(gt, lt, group=self.group)
+        else:
+            self.dist.all_gather(list(gt.view(self.world, -1).unbind(0)), lt, group=self.group)
 
-
-def _partial(local: PDL, op: str, offset: int):
-    """One 32-byte record for this rank's block (flattened): value bits, good count, GLOBAL index,
-    state (0 no good element, 1 value is non-NaN, 2 value is NaN)."""
-    flat = local.flat()
-    rec = np.zeros((), dtype=_REC)
-    if flat.nelem == 0:
-        return rec
-    ngood = int(ufunc.ngoodover(flat).sclr())
-    rec["ngood"] = ngood
-    if ngood == 0:
-        return rec
-    if op in ("sum", "avg"):
-        v = ufunc.sumover(flat)
-        rec["val"] = T.value_bits(v.datatype, v.sclr())
-        rec["state"] = 1
-    else:
-        red, ind = (ufunc.minimum, ufunc.minimum_ind) if op in ("min", "min_ind") else (ufunc.maximum, ufunc.maximum_ind)
-        v = red(flat)
-        val = v.sclr()
-        rec["val"] = T.value_bits(v.datatype, val)
-        rec["idx"] = int(ind(flat).sclr()) + offset
-        rec["state"] = 2 if (v.datatype in (T.F, T.D) and val != val) else 1
-    return rec
-
-
-def _finish(recs: np.ndarray, op: str, dtype_id: int):
-    """Merge the per-rank records in rank order.  Returns (value, is_bad)."""
-    dt = T.NP_DTYPE[dtype_id]
-    live = [r for r in recs if r["ngood"] > 0]
-    if not live:
-        return None, True
-    vals = [T.bits_value(dtype_id, int(r["val"])) for r in live]
-    if op in ("sum", "avg"):
-        with np.errstate(over="ignore"):
-            tot = vals[0]
-            for v in vals[1:]:
-                tot = dt.type(tot + v)
-        if op == "sum":
-            return tot, False
-        cnt = int(sum(int(r["ngood"]) for r in live))
-        if dt.kind == "f":
-            return dt.type(tot / dt.type(cnt)), False
-        if dtype_id == T.ULL:
-            return dt.type(int(tot) // cnt), False
-        q = abs(int(tot)) // cnt
-        return dt.type(q if int(tot) >= 0 else -q), False       # C division truncates toward zero
-    ismax = op in ("max", "max_ind")
-    best = None
-    for r, v in zip(live, vals):
-        if best is None:
-            best = (r, v)
-            continue
-        br, bv = best
-        if br["state"] == 1 and r["state"] == 1:
-            better = (v > bv) if ismax else (v < bv)
-            if better or (v == bv and r["idx"] < br["idx"]):
-                best = (r, v)
-        elif br["state"] == 2 and r["state"] == 1:
-            best = (r, v)
-        elif br["state"] == 2 and r["state"] == 2 and r["idx"] > br["idx"]:
-            best = (r, v)       # every good value is NaN: the reference ends on the LAST one
-    r, v = best
-    if op.endswith("_ind"):
-        return np.int64(r["idx"]), False
-    return v, False
+    def block_offset(self, n_local: int):
+        """(global index of this rank's element 0, total length) for blocks laid end to end in rank order.
+        One small host collective; pass offset=/total= to the reductions to skip it."""
+        sizes = self.all_gather_bytes(np.array([n_local], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
+        return int(sizes[:self.rank].sum()), int(sizes.sum())
 
 
-def _collapse(local: PDL, comm: Comm, op: str, out_type: int, offset: int | None = None) -> PDL:
-    if offset is None:  # global flat index of this rank's first element: exclusive scan of block sizes
-        sizes = comm.all_gather_bytes(np.array([local.nelem], dtype=np.int64).view(np.uint8)).view(np.int64).reshape(-1)
-        offset = int(sizes[:comm.rank].sum())
-    rec = _partial(local, op, offset)
-    recs = comm.all_gather_bytes(np.frombuffer(rec.tobytes(), dtype=np.uint8)).view(_REC).reshape(-1)
-    val, bad = _finish(recs, op, out_type if not op.endswith("_ind") else local.datatype)
-    res_type = T.IND if op.endswith("_ind") else out_type
-    if bad:
-        val = T.DEFAULT_BAD[res_type]
-    out = PDL.from_numpy(np.array(val, dtype=T.NP_DTYPE[res_type]), res_type, local.engine)
-    out.badflag = bool(bad) or local.badflag
-    return out
+# kind -> (PART op that makes its record, value type of the record)
+def _part_of(kind: str, t: int):
+    if kind in ("sum", "avg"):
+        return "part_sum", T.int_plus(t)
+    if kind in ("dsum", "davg"):
+        return "part_dsum", T.D
+    if kind in ("min", "min_ind"):
+        return "part_min", t
+    if kind in ("max", "max_ind"):
+        return "part_max", t
+    raise PDLError(f"unknown sharded reduction '{kind}'")
 
 
-def psum(local: PDL, comm: Comm) -> PDL:
+_COLL_OF = {"sum": "sum", "dsum": "sum", "avg": "avg", "davg": "avg", "min": "min", "max": "max",
+            "min_ind": "min_ind", "max_ind": "max_ind"}
+
+
+def pcollapse(local: PDL, comm: Comm, kinds, offset: int | None = None, total: int | None = None) -> list:
+    """Reductions over dim 0 of an ndarray whose dim 0 is SHARDED across `comm` (blocks in rank order):
+    `local` is this rank's block [n_local, rows...]; returns one [rows...] ndarray per entry of `kinds`
+    ('sum' 'avg' 'dsum' 'davg' 'min' 'max' 'min_ind' 'max_ind'), identical bits on every rank.
+
+    Everything stays on the device and on the engine's stream: one PART_* launch per distinct partial
+    (sum+avg share one pass, max+max_ind too) writes 32-byte records, ONE all-gather moves the records of all
+    kinds, one COLL_* launch per kind merges them in rank order with the reference's BAD / NaN / first-index
+    rules (include/pdlb200.h).  No host synchronisation unless `offset` has to be discovered."""
+    from .trans import run_op, collapse_records
+    if local.ndims < 1:
+        local = local.dummy(0)
+    n_local, rows = local.dims[0], local.dims[1:]
+    if offset is None:
+        offset, total = comm.block_offset(n_local)
+    nrows = 1
+    for d in rows:
+        nrows *= d
+    parts = []                                   # distinct partial ops, in first-use order
+    for k in kinds:
+        pk = _part_of(k, local.datatype)
+        if pk not in parts:
+            parts.append(pk)
+    nwords = 4 * len(parts) * nrows
+    lt, gt, lrec, grec = comm.record_buffers(local.engine, nwords)
+    lview = lrec.reshape_view([4, len(parts)] + rows)
+    for j, (pname, _vt) in enumerate(parts):
+        run_op(pname, [local], [lview.slice(f":,({j})")], goff=offset)
+    comm.all_gather_records(local.engine, lt, gt)
+    gview = grec.reshape_view([4, len(parts)] + rows + [comm.world])
+    outs = []
+    for k in kinds:
+        pk = _part_of(k, local.datatype)
+        recs = gview.slice(f":,({parts.index(pk)})").mv(-1, 1)      # [4, world, rows...]
+        out = collapse_records(_COLL_OF[k], recs, pk[1], local.badflag)
+        if total == 0 and k in ("min", "max", "min_ind", "max_ind"):
+            out.badflag = True                   # no element anywhere: BAD + badflag even in good mode (Ufunc.pd:463-464)
+        outs.append(out)
+    return outs
+
+
+def _whole(local: PDL, comm: Comm, kind: str, offset=None, total=None) -> PDL:
+    """Whole-array wrapper (`$x->flat->Xover`, lib/PDL/Ufunc.pd:618-663) of an ndarray sharded along its
+    outermost dim: the local block is a contiguous run of the global flat ndarray."""
+    return pcollapse(local.flat(), comm, (kind,), offset, total)[0]
+
+
+def psum(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
     """sum() of an ndarray sharded across comm (flat->sumover + collapse of the sharded dim)."""
-    return _collapse(local, comm, "sum", T.int_plus(local.datatype))
+    return _whole(local, comm, "sum", offset, total)
 
 
-def pavg(local: PDL, comm: Comm) -> PDL:
-    return _collapse(local, comm, "avg", T.int_plus(local.datatype))
+def pavg(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    return _whole(local, comm, "avg", offset, total)
 
 
-def pmin(local: PDL, comm: Comm) -> PDL:
-    return _collapse(local, comm, "min", local.datatype)
+def pmin(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    return _whole(local, comm, "min", offset, total)
 
 
-def pmax(local: PDL, comm: Comm) -> PDL:
-    return _collapse(local, comm, "max", local.datatype)
+def pmax(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    return _whole(local, comm, "max", offset, total)
 
 
-def pmin_ind(local: PDL, comm: Comm) -> PDL:
-    return _collapse(local, comm, "min_ind", local.datatype)
+def pmin_ind(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    return _whole(local, comm, "min_ind", offset, total)
 
 
-def pmax_ind(local: PDL, comm: Comm) -> PDL:
-    return _collapse(local, comm, "max_ind", local.datatype)
+def pmax_ind(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    return _whole(local, comm, "max_ind", offset, total)
+
+
+def psumover(local: PDL, comm: Comm, offset=None, total=None) -> PDL:
+    """sumover of an ndarray whose REDUCED dim (dim 0) is the sharded one."""
+    return pcollapse(local, comm, ("sum",), offset, total)[0]
 
 
 def pminmax(local: PDL, comm: Comm):
@@ -231,4 +249,4 @@ def pinner(a_local: PDL, b_local: PDL, comm: Comm) -> PDL:
     return out
 
 
-__all__ = ["split_dim", "shard", "Comm", "psum", "pavg", "pmin", "pmax", "pmin_ind", "pmax_ind", "pminmax", "pinner"]
+__all__ = ["split_dim", "shard", "Comm", "pcollapse", "psumover", "psum", "pavg", "pmin", "pmax", "pmin_ind", "pmax_ind", "pminmax", "pinner"]

@@ -38,6 +38,7 @@ class OpSpec:
     gentypes: tuple             # GenericTypes, in declaration order (last = fallback)
     kind: str                   # biop | bifunc | ufunc | reduce | matmult | convert
     inplace: tuple = ()         # parameter names that may run in place
+    fixed: tuple = ()           # named dims of fixed size, e.g. (("r", 4),)
     opid: int = field(init=False)
 
     def __post_init__(self):
@@ -121,6 +122,9 @@ SPECS = {s.name: s for s in [
     OpSpec("axisvalues", [Par("i", ("n",)), Par("a", ("n",), out=True)], _A, "axis", inplace=("i",)),
     OpSpec("inner", [Par("a", ("n",)), Par("b", ("n",)), Par("c", out=True)], _A, "inner"),
     OpSpec("outer", [Par("a", ("n",)), Par("b", ("m",)), Par("c", ("n", "m"), out=True)], _A, "outer"),
+    # per-rank partial records of a sharded whole-array reduction (include/pdlb200.h PART_*): a(n); longlong [o]rec(r=4)
+    *[OpSpec(n, [Par("a", ("n",)), Par("rec", ("r",), out=True, typed=T.LL)], g, "part", fixed=(("r", 4),))
+      for n, g in (("part_sum", _A), ("part_dsum", _R), ("part_min", _R), ("part_max", _R))],
     # matmult, lib/PDL/Primitive.pd:191-195
     OpSpec("matmult", [Par("a", ("t", "h")), Par("b", ("w", "t")), Par("c", ("w", "h"), out=True)], _A, "matmult"),
 ]}
@@ -316,7 +320,8 @@ def prepare_op(name: str, inputs: list, outputs: list | None = None, param: floa
     return run_op(name, inputs, outputs, _prepare=True, param=param)
 
 
-def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False, param: float = 0.0):
+def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False, param: float = 0.0,
+           goff: int = 0):
     """pdl_run_<name>(inputs..., outputs...).  `outputs` entries may be None (null ndarray:
     created with the broadcast dims).  Returns the output ndarrays."""
     spec = SPECS[name]
@@ -345,7 +350,7 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     bval = any(x.badflag for x in ins)
 
     # named dims (pdl_dim_checks): inputs define them; size-1 stretches; missing dims promote to 1
-    ind: dict = {}
+    ind: dict = dict(spec.fixed)
     for x, par in zip(ins, in_pars):
         for j, dn in enumerate(par.realdims):
             sz = x.dims[j] if j < x.ndims else 1
@@ -406,6 +411,9 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     elif spec.kind == "inner":
         a, b, _c = placeholder
         named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0)]}
+    elif spec.kind == "part":
+        a, rec = placeholder
+        named = {"ind": [ind["n"], int(goff)], "rinc": [_real_inc(a, 0), _real_inc(rec, 0)]}
     if spec.kind == "reduce":
         a = placeholder[0]
         named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0)]}
@@ -448,7 +456,46 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     return final_outs
 
 
+_COLL = {}
+for _k in ("sum", "avg", "min", "max", "min_ind", "max_ind"):
+    _c = OpSpec.__new__(OpSpec)
+    _c.name, _c.kind, _c.opid = "coll_" + _k, "coll", _abi.OPS["coll_" + _k]
+    _c.pars, _c.gentypes, _c.inplace, _c.fixed = [Par("rec", ("r", "k"), typed=T.LL), Par("b", out=True)], T.ALL, (), (("r", 4),)
+    _COLL[_k] = _c
+
+
+def collapse_records(kind: str, recs: PDL, value_type: int, bval: bool) -> PDL:
+    """COLL_<kind> (include/pdlb200.h): recs = longlong [4, k, rows...], the k per-rank records of every row;
+    returns the merged [rows...] ndarray (type: `value_type`, or indx for the _ind kinds).  ONE launch."""
+    spec = _COLL[kind]
+    if recs.datatype not in (T.LL, T.IND) or recs.ndims < 2 or recs.dims[0] != 4:
+        raise PDLError(f"PDL::{spec.name}: records must be longlong [4, k, ...]")
+    out = PDL.empty(T.IND if kind.endswith("_ind") else value_type, recs.dims[2:], recs.engine)
+    out.badflag = bool(bval)
+    bc = _broadcast([recs, out], [2, 0], [False, False], spec.name)
+    named = {"ind": [recs.dims[1]], "rinc": [_real_inc(recs, 0), _real_inc(recs, 1)]}
+    _launch(spec, value_type, [recs, out], bc, named, bval)
+    return out
+
+
 # ---- the three generator shapes of Ops.pd ----------------------------------------------------
+
+# ops whose deferred form a following reduction knows how to absorb (SURVEY.md §8(f)4)
+_DEFERRABLE = ("mult",)
+
+
+def _deferred(name: str, a: PDL, b: PDL) -> PDL:
+    """make_trans_mutual with PDL_ITRANS_DO_DATAFLOW_F (pdlapi.c:781-801): types, dims and flags of the child
+    are settled now, readdata is NOT run — the child keeps the transformation as `_pending`."""
+    spec = SPECS[name]
+    transtype = transtype_select(spec, [a, b, None])
+    ins = [x if x.datatype == transtype else convert_type(x, transtype) for x in (a, b)]
+    bc = _broadcast(ins + [ins[0]], [0, 0, 0], [False, False, True], name)
+    out = PDL(a.engine, None, transtype, bc.dims[:bc.nimpl])
+    out.badflag = any(x.badflag for x in ins)
+    out._pending = (name, ins)
+    return out
+
 
 def run_biop(name: str, a, b, c=None, swap: int = 0) -> PDL:
     """XS PDL::<name>(a,b,[c],swap): swap a/b, then PDL_XS_INPLACE (lib/PDL/Ops.pd:108-114,
@@ -460,7 +507,26 @@ def run_biop(name: str, a, b, c=None, swap: int = 0) -> PDL:
     if c is None and a.is_inplace():
         a._inplace = False
         c = a
+    if c is None and name in _DEFERRABLE and (a._flowing or b._flowing) and T.is_device_type(a.datatype) and T.is_device_type(b.datatype):
+        return _deferred(name, a, b)
     return run_op(name, [a, b], [c])[0]
+
+
+def fused_reduction(name: str, x: PDL):
+    """`($a->flowing * $b)->sumover`: the product's readdata was deferred and the reduction is its consumer, so
+    the pair runs as ONE launch of the fused kernel (`inner`, lib/PDL/Primitive.pd:48-70 = sum_n a*b) and the
+    intermediate ndarray is never written.  Only where the fused form has the unfused one's semantics: no BAD
+    values (inner makes a row with a BAD element BAD, sumover skips it), float/double (for the small integer
+    types sumover widens to `int+`, inner does not).  Returns None when the pair does not qualify."""
+    if name != "sumover" or x._pending is None or x._pending[0] != "mult":
+        return None
+    a, b = x._pending[1]
+    if a.badflag or b.badflag or x.datatype not in (T.F, T.D) or x.ndims < 1:
+        return None
+    # the reduced dim is dim 0 of the PRODUCT: give both operands that dim explicitly (size 1 = stretches)
+    a1 = a if a.ndims >= 1 else a.dummy(0)
+    b1 = b if b.ndims >= 1 else b.dummy(0)
+    return run_op("inner", [a1, b1], [None])[0]
 
 
 def run_ufunc(name: str, a, b=None) -> PDL:

@@ -2,7 +2,7 @@
 dim 0 and the whole-array wrappers `sum max ...` = `$x->flat->Xover` (Ufunc.pd:618-663)."""
 from __future__ import annotations
 
-from .trans import run_op, as_pdl
+from .trans import run_op, as_pdl, fused_reduction
 
 _REDUCERS = ["sumover", "prodover", "dsumover", "dprodover", "average", "daverage",
              "minimum", "maximum", "minimum_ind", "maximum_ind",
@@ -12,7 +12,12 @@ _REDUCERS = ["sumover", "prodover", "dsumover", "dprodover", "average", "daverag
 
 def _mk(name):
     def f(a, b=None):
-        return run_op(name, [as_pdl(a)], [b])[0]
+        a = as_pdl(a)
+        if b is None and a._pending is not None:      # deferred producer (->flowing): try the fused form first
+            r = fused_reduction(name, a)
+            if r is not None:
+                return r
+        return run_op(name, [a], [b])[0]
     f.__name__ = name
     f.__doc__ = f"PDL::{name}(a(n); [o]b()) — lib/PDL/Ufunc.pd"
     return f

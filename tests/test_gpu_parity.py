@@ -463,6 +463,60 @@ def test_outer(engines, t):
     assert P.outer(g1, g2).to_numpy().tobytes() == (g1.dummy(1, 1) * g2.dummy(0, 1)).to_numpy().tobytes()
 
 
+def test_inner_magnover_nonfinite_and_overflow(engines):
+    """The reference accumulates in long double and carries inf / NaN through; the compensated device sum must
+    not turn an infinite total into NaN (round-1 advisor finding)."""
+    inf, nan = np.inf, np.nan
+    rows = np.array([[1.0, inf, 2.0, 3.0], [1e308, 1e308, 1e308, 1.0], [inf, -inf, 1.0, 1.0],
+                     [-inf, 5.0, 1.0, 1.0], [nan, 1.0, 2.0, 3.0], [1.0, 2.0, 3.0, 4.0]])
+    ones = np.ones_like(rows)
+    for t in (T.D, T.F):
+        r = rows if t == T.D else np.where(np.abs(rows) == 1e308, 3e38, rows)
+        (ga, oa), (gb, ob) = both(engines, r, t), both(engines, ones * 2, t)
+        assert_same(f"inner-nonfinite-{T.NAMES[t]}", P.inner(ga, gb), P.inner(oa, ob), nan_equal=True)
+        assert_same(f"magnover-nonfinite-{T.NAMES[t]}", ufunc.magnover(ga), ufunc.magnover(oa), nan_equal=True)
+    big = np.tile(rows, (1, 5000))                         # long rows: the warp/CTA kernels and their merges
+    (ga, oa), (gb, ob) = both(engines, big, T.D), both(engines, np.ones_like(big), T.D)
+    assert_same("inner-nonfinite-long", P.inner(ga, gb), P.inner(oa, ob), nan_equal=True)
+    assert_same("magnover-nonfinite-long", ufunc.magnover(ga), ufunc.magnover(oa), nan_equal=True)
+
+
+def test_matmult_more_than_65535_batches(engines):
+    """Batches of small matrices, (3,3,70000) x (3,3,70000): the broadcast positions exceed gridDim.z."""
+    rng = np.random.default_rng(77)
+    for t in (T.D, T.F, T.L):
+        a = rand_array(rng, t, (70000, 3, 3), "small")
+        b = rand_array(rng, t, (70000, 3, 3), "small")
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"matmult-batch-{T.NAMES[t]}", P.matmult(ga, gb), P.matmult(oa, ob))
+    a = rng.integers(-8, 8, size=(66000, 64, 16)).astype(np.float64)      # DMMA-eligible tiles, > 65535 of them
+    b = rng.integers(-8, 8, size=(16, 64)).astype(np.float64)
+    (ga, oa), (gb, ob) = both(engines, a, T.D), both(engines, b, T.D)
+    assert_same("matmult-dmma-batch", P.matmult(ga, gb), P.matmult(oa, ob))
+
+
+def test_flowing_product_fused_into_sumover(engines):
+    cuda = engines[0]
+    rng = np.random.default_rng(12)
+    for t in (T.D, T.F):
+        # double: products and sums exact (SURVEY.md 8(d) cfg3 values); float: small integers, so that the unfused
+        # float accumulation is exact too (otherwise fused, which accumulates in double, is the MORE accurate one)
+        big1, big2 = rng.integers(-1024, 1024, size=4000) / 256, rng.integers(-1024, 1024, size=1000) / 256
+        if t == T.F:
+            big1, big2 = np.round(big1 * 2), np.round(big2 * 2)
+        res = []
+        for e in engines:
+            a = P.PDL.from_numpy(big1, t, e).slice("0:-1:2").dummy(1, 1)
+            b = P.PDL.from_numpy(big2, t, e).slice("0:-1:2").dummy(0, 1)
+            l0 = cuda.launch_count()
+            fused = ufunc.sumover(a.flowing() * b)
+            if e is cuda:
+                assert cuda.last_kernel() == "inner" and cuda.launch_count() - l0 <= 2    # inner (+ its finish), no mult
+            res.append((fused, ufunc.sumover(a * b)))
+        assert_same(f"fused-{T.NAMES[t]}", res[0][0], res[1][0])
+        assert_same(f"fused-vs-unfused-{T.NAMES[t]}", res[0][0], res[0][1])
+
+
 @pytest.mark.parametrize("t", [T.SB, T.B, T.S, T.US], ids=lambda t: T.NAMES[t])
 def test_small_int_divide_sqrt_exhaustive(engines, t):
     """8-bit divide runs on one approximate float division and 8/16-bit sqrt on the float square root:

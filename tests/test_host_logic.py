@@ -138,3 +138,36 @@ def test_prepared_ops_apply_output_state_rules(oracle_engine):
     out4 = P.PDL.empty(T.F, [3], e)
     P.prepare_op("setbadtoval", [b], [out4])()
     assert not out4.badflag
+
+
+def test_flowing_defers_readdata_and_fuses_into_sumover(oracle_engine):
+    """`$a->flowing * $b` defers the product's readdata (pdlapi.c:781-801); `->sumover` as its consumer runs the
+    pair as ONE transformation (inner); anything else that needs the data runs the deferred readdata first."""
+    e = oracle_engine
+    rng = np.random.default_rng(8)
+    a = P.PDL.from_numpy(rng.integers(-1024, 1024, size=64) / 256, T.D, e).slice("0:-1:2").dummy(1, 1)
+    b = P.PDL.from_numpy(rng.integers(-1024, 1024, size=40) / 256, T.D, e).slice("0:-1:2").dummy(0, 1)
+    c0 = e.calls
+    unfused = ufunc.sumover(a * b)
+    assert e.calls - c0 == 2
+    c0 = e.calls
+    fused = ufunc.sumover(a.flowing() * b)
+    assert e.calls - c0 == 1                                   # one launch, no intermediate
+    assert fused.dims == unfused.dims and fused.type == unfused.type
+    assert fused.to_numpy().tobytes() == unfused.to_numpy().tobytes()
+    # the deferred product is an ordinary ndarray as soon as anyone else looks at it
+    prod = a.flowing() * b
+    assert prod.is_pending() and prod.dims == [32, 20]
+    c0 = e.calls
+    assert prod.to_numpy().tobytes() == (a * b).to_numpy().tobytes()
+    assert not prod.is_pending()
+    # not fused where the fused form would change the answer: BAD values (sumover skips, inner poisons), small ints
+    ab = P.PDL.from_numpy(np.array([1, 2, 3, -3.4028234663852886e38], dtype=np.float32), T.F, e).set_badflag(True)
+    r = ufunc.sumover(ab.flowing() * ab)
+    assert r.badflag and r.sclr() == 14.0
+    ai = P.PDL.from_numpy(np.array([100, 100, 100], dtype=np.int16), T.S, e)
+    r = ufunc.sumover(ai.flowing() * ai)
+    assert r.type == "long" and r.sclr() == 30000
+    # the flag applies to the NEXT operation only
+    f = a.flowing()
+    assert (f * b).is_pending() and not (a * b).is_pending()

@@ -61,6 +61,18 @@ def _worker(rank, world, port, q):
                 res[f"{name}-{T.NAMES[t]}"] = g.tobytes().hex()
             gi = parallel.pmax_ind(mine, comm).sclr()
             assert gi == ufunc.maximum_ind(whole.flat()).sclr(), ("max_ind", T.NAMES[t])
+            # several reductions in ONE exchange, explicit offset/total (no host collective at all)
+            blocks = parallel.split_dim(whole.dims[-1], world)
+            off = sum(c for _, c in blocks[:rank]) * whole.dims[0]
+            many = parallel.pcollapse(mine.flat(), comm, ("dsum", "davg", "min_ind", "sum"), offset=off, total=whole.nelem)
+            for o, f in zip(many, (ufunc.dsumover, ufunc.daverage, ufunc.minimum_ind, ufunc.sumover)):
+                e = f(whole.flat())
+                assert o.type == e.type and o.badflag == e.badflag
+                assert o.to_numpy().tobytes() == e.to_numpy().tobytes() or np.isnan(o.to_numpy()), (f.__name__, T.NAMES[t])
+            # the REDUCED dim is the sharded one: one record per row, result has the row dims
+            xw = whole.xchg(0, 1)
+            rows = parallel.psumover(parallel.shard(xw, rank, world, dim=0), comm)
+            assert rows.dims == [whole.dims[0]] and rows.to_numpy().tobytes() == ufunc.sumover(xw).to_numpy().tobytes()
             # minmax in one local pass (minmaximum) + merge; inner of two identically sharded ndarrays
             gmn, gmx = parallel.pminmax(mine, comm)
             emn, emx, _, _ = ufunc.minmaximum(whole.flat())
