@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
 
 def test_plumbing_without_gpu():
     lib = _abi.load()
-    assert lib.pdlb200_abi_version() == 3
+    assert lib.pdlb200_abi_version() == _abi.ABI_VERSION == 4
     assert lib.pdlb200_type_size(10) == 8 and lib.pdlb200_type_size(0) == 1
     assert lib.pdlb200_op_name(30) == b"sumover"
     if lib.pdlb200_device_count() > 0:
