@@ -221,6 +221,35 @@ PDLB200_API void   pdlb200_managed_trim(void);      /* hand every cached block b
 PDLB200_API int    pdlb200_ptr_kind(const void *p);
 /* Migrate a managed range towards the device (to_device != 0) or the host ahead of use. */
 PDLB200_API int    pdlb200_prefetch(void *p, size_t nbytes, int to_device, void *stream, char *err, size_t errlen);
+/* --- coherent host/device store for an UNMODIFIED host core (north-star subsystem 1) -------------------------
+ * What the reference-side binding (perl/PDL-B200) backs ndarray data with.  One buffer = a cudaMalloc'd
+ * (stream-ordered pool) device allocation + a page-aligned host MIRROR of the same size, which is what the host
+ * core sees as pdl->data (replaces the SV of pdl_allocdata, lib/PDL/Core/pdlapi.c:172-209) + host/device dirty
+ * bits.  While the mirror is not current its pages are PROT_NONE: the binding makes it current explicitly at the
+ * reference's host-access choke points it can see (pdlb200_mbuf_host), and ANY other host dereference
+ * (lib/PDL/Core.xs:771-859,1045,1145-1199, pdlconv.c:6-43, CPU readdata bodies) faults into the library's
+ * SIGSEGV handler, which does the same — stream sync, one D2H copy of the buffer, mprotect — and resumes; a
+ * host WRITE additionally marks the device copy stale (re-uploaded by the next device op that reads it).
+ * Chained device ops never cross PCIe and never synchronise.  Freed buffers are recycled by exact size. */
+/* New buffer (contents undefined, mirror not current).  Returns the MIRROR address (the handle), NULL on failure. */
+PDLB200_API void  *pdlb200_mbuf_new(size_t nbytes);
+/* New buffer whose device copy holds `nbytes` from plain host memory `src` (one H2D copy; `src` may be released
+ * on return).  The mirror is not populated. */
+PDLB200_API void  *pdlb200_mbuf_adopt(const void *src, size_t nbytes, char *err, size_t errlen);
+PDLB200_API void   pdlb200_mbuf_retain(void *mirror);   /* one more owner (an aliasing view, e.g. clump of a physical parent) */
+PDLB200_API void   pdlb200_mbuf_free(void *mirror);     /* drop one owner; the last one recycles the buffer */
+PDLB200_API int    pdlb200_mbuf_is(const void *mirror); /* 1 iff `mirror` is the base address of a live store buffer */
+/* Device pointer for a kernel launched on `stream`.  A stale device copy is uploaded first unless `discard`
+ * (the kernel overwrites the whole buffer); `for_write` marks the mirror stale. */
+PDLB200_API void  *pdlb200_mbuf_dev(void *mirror, int for_write, int discard, void *stream, char *err, size_t errlen);
+/* Make the mirror current (download iff the device copy is newer); `for_write` marks the device copy stale.
+ * No-op (OK) for pointers that are not store buffers. */
+PDLB200_API int    pdlb200_mbuf_host(void *mirror, int for_write, char *err, size_t errlen);
+/* -1 not a store buffer; else bit0-1 host state (0 stale, 1 current clean, 2 current + host-modified), bit2 device copy current */
+PDLB200_API int    pdlb200_mbuf_state(const void *mirror);
+/* out[8] = buffers created, recycled, uploads, upload bytes, downloads, download bytes, faults handled, adopted */
+PDLB200_API void   pdlb200_mbuf_stats(uint64_t *out);
+PDLB200_API void   pdlb200_mbuf_trim(void);            /* hand every cached buffer back to the driver / the OS */
 /* Number of kernels this library has launched in this process (bench "gpu_launches"). */
 PDLB200_API uint64_t pdlb200_launch_count(void);
 /* Name of the kernel variant chosen by the most recent launch on this thread (introspection,

@@ -79,6 +79,8 @@ SYMBOLS = [
     "pdlb200_memcpy_d2h", "pdlb200_managed_alloc", "pdlb200_managed_free", "pdlb200_managed_trim", "pdlb200_ptr_kind",
     "pdlb200_prefetch", "pdlb200_launch_count", "pdlb200_last_kernel", "pdlb200_op_name",
     "pdlb200_type_size",
+    "pdlb200_mbuf_new", "pdlb200_mbuf_adopt", "pdlb200_mbuf_retain", "pdlb200_mbuf_free", "pdlb200_mbuf_is",
+    "pdlb200_mbuf_dev", "pdlb200_mbuf_host", "pdlb200_mbuf_state", "pdlb200_mbuf_stats", "pdlb200_mbuf_trim",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpdlb200.so"
@@ -149,5 +151,23 @@ def load():
     lib.pdlb200_op_name.restype = C.c_char_p
     lib.pdlb200_type_size.argtypes = [C.c_int]
     lib.pdlb200_type_size.restype = C.c_size_t
+    lib.pdlb200_mbuf_new.argtypes = [C.c_size_t]
+    lib.pdlb200_mbuf_new.restype = C.c_void_p
+    lib.pdlb200_mbuf_adopt.argtypes = [C.c_void_p, C.c_size_t] + errargs
+    lib.pdlb200_mbuf_adopt.restype = C.c_void_p
+    for name in ("pdlb200_mbuf_retain", "pdlb200_mbuf_free"):
+        getattr(lib, name).argtypes = [C.c_void_p]
+        getattr(lib, name).restype = None
+    lib.pdlb200_mbuf_is.argtypes = [C.c_void_p]
+    lib.pdlb200_mbuf_is.restype = C.c_int
+    lib.pdlb200_mbuf_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + errargs
+    lib.pdlb200_mbuf_dev.restype = C.c_void_p
+    lib.pdlb200_mbuf_host.argtypes = [C.c_void_p, C.c_int] + errargs
+    lib.pdlb200_mbuf_host.restype = C.c_int
+    lib.pdlb200_mbuf_state.argtypes = [C.c_void_p]
+    lib.pdlb200_mbuf_state.restype = C.c_int
+    lib.pdlb200_mbuf_stats.argtypes = [C.POINTER(C.c_uint64)]
+    lib.pdlb200_mbuf_stats.restype = None
+    lib.pdlb200_mbuf_trim.restype = None
     _lib = lib
     return lib
