@@ -113,6 +113,11 @@ enum {
   PDLB200_OP_PART_SUM = 80, PDLB200_OP_PART_DSUM, PDLB200_OP_PART_MIN, PDLB200_OP_PART_MAX,
   PDLB200_OP_COLL_SUM = 84, PDLB200_OP_COLL_AVG, PDLB200_OP_COLL_MIN, PDLB200_OP_COLL_MAX,
   PDLB200_OP_COLL_MIN_IND, PDLB200_OP_COLL_MAX_IND,
+  /* minimum_n_ind / maximum_n_ind, lib/PDL/Ufunc.pd:502-561 : a(n); indx [o]c(m) — indices of the first m extreme
+   * elements (m selection passes with minimum_ind's rule).  ind = {n, m}, rinc = {inc_a_n, inc_c_m}.  Slots that
+   * cannot be filled are BAD and flag the output: `anybad` (required) reports that; otherwise the output's
+   * badflag is CLEARED ($PDLSTATESETGOOD, Ufunc.pd:521). */
+  PDLB200_OP_MINIMUM_N_IND = 90, PDLB200_OP_MAXIMUM_N_IND = 91,
   PDLB200_OP__END
 };
 
@@ -198,6 +203,11 @@ PDLB200_API int    pdlb200_buf_upload(pdlb200_buf *b, const void *host, size_t n
 /* Device -> host iff the device copy is newer (or force != 0); synchronises the stream. */
 PDLB200_API int    pdlb200_buf_download(pdlb200_buf *b, void *host, size_t nbytes, int force, void *stream, char *err, size_t errlen);
 PDLB200_API int    pdlb200_buf_device_dirty(const pdlb200_buf *b);
+/* The allocator under the store, usable directly: device memory without zero-fill from an exact-size free list in
+ * front of the stream-ordered pool (a recycled block costs a hash lookup).  `nbytes` of free must be the allocation's. */
+PDLB200_API void  *pdlb200_dev_alloc(size_t nbytes);
+PDLB200_API void   pdlb200_dev_free(void *p, size_t nbytes);
+PDLB200_API void   pdlb200_dev_trim(void);            /* hand the cached blocks back to the pool */
 
 /* --- plumbing ------------------------------------------------------------- */
 PDLB200_API int    pdlb200_abi_version(void);
@@ -250,6 +260,11 @@ PDLB200_API int    pdlb200_mbuf_state(const void *mirror);
 /* out[8] = buffers created, recycled, uploads, upload bytes, downloads, download bytes, faults handled, adopted */
 PDLB200_API void   pdlb200_mbuf_stats(uint64_t *out);
 PDLB200_API void   pdlb200_mbuf_trim(void);            /* hand every cached buffer back to the driver / the OS */
+/* Which transformation vtables of the host core run on the device: the binding registers them when it attaches
+ * and asks from its PDL->make_trans_mutual wrapper (everything else is a CPU op whose parameters must be made
+ * current in host memory first).  Opaque pointers. */
+PDLB200_API void   pdlb200_devop_register(const void *vtable, int on);
+PDLB200_API int    pdlb200_devop_is(const void *vtable);
 /* Number of kernels this library has launched in this process (bench "gpu_launches"). */
 PDLB200_API uint64_t pdlb200_launch_count(void);
 /* Name of the kernel variant chosen by the most recent launch on this thread (introspection,

@@ -66,6 +66,7 @@ OPS = {
     # sharded whole-array reductions: per-rank partial records and their rank-ordered merge
     "part_sum": 80, "part_dsum": 81, "part_min": 82, "part_max": 83,
     "coll_sum": 84, "coll_avg": 85, "coll_min": 86, "coll_max": 87, "coll_min_ind": 88, "coll_max_ind": 89,
+    "minimum_n_ind": 90, "maximum_n_ind": 91,
 }
 ABI_VERSION = 4
 
@@ -81,6 +82,7 @@ SYMBOLS = [
     "pdlb200_type_size",
     "pdlb200_mbuf_new", "pdlb200_mbuf_adopt", "pdlb200_mbuf_retain", "pdlb200_mbuf_free", "pdlb200_mbuf_is",
     "pdlb200_mbuf_dev", "pdlb200_mbuf_host", "pdlb200_mbuf_state", "pdlb200_mbuf_stats", "pdlb200_mbuf_trim",
+    "pdlb200_devop_register", "pdlb200_devop_is", "pdlb200_dev_alloc", "pdlb200_dev_free", "pdlb200_dev_trim",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpdlb200.so"
@@ -151,6 +153,11 @@ def load():
     lib.pdlb200_op_name.restype = C.c_char_p
     lib.pdlb200_type_size.argtypes = [C.c_int]
     lib.pdlb200_type_size.restype = C.c_size_t
+    lib.pdlb200_dev_alloc.argtypes = [C.c_size_t]
+    lib.pdlb200_dev_alloc.restype = C.c_void_p
+    lib.pdlb200_dev_free.argtypes = [C.c_void_p, C.c_size_t]
+    lib.pdlb200_dev_free.restype = None
+    lib.pdlb200_dev_trim.restype = None
     lib.pdlb200_mbuf_new.argtypes = [C.c_size_t]
     lib.pdlb200_mbuf_new.restype = C.c_void_p
     lib.pdlb200_mbuf_adopt.argtypes = [C.c_void_p, C.c_size_t] + errargs

@@ -103,6 +103,7 @@ static void init_names() {
   N(PDLB200_OP_PART_MAX, "part_max") N(PDLB200_OP_COLL_SUM, "coll_sum") N(PDLB200_OP_COLL_AVG, "coll_avg")
   N(PDLB200_OP_COLL_MIN, "coll_min") N(PDLB200_OP_COLL_MAX, "coll_max") N(PDLB200_OP_COLL_MIN_IND, "coll_min_ind")
   N(PDLB200_OP_COLL_MAX_IND, "coll_max_ind")
+  N(PDLB200_OP_MINIMUM_N_IND, "minimum_n_ind") N(PDLB200_OP_MAXIMUM_N_IND, "maximum_n_ind")
 #undef N
 }
 
@@ -196,6 +197,7 @@ int pdlb200_reduce(const pdlb200_trans *t, char *err, size_t errlen) {
   if (t->op == PDLB200_OP_MAGNOVER) return launch_magnover(t, E);
   if (t->op >= PDLB200_OP_PART_SUM && t->op <= PDLB200_OP_PART_MAX) return launch_partial(t, E);
   if (t->op >= PDLB200_OP_COLL_SUM && t->op <= PDLB200_OP_COLL_MAX_IND) return launch_collapse(t, E);
+  if (t->op == PDLB200_OP_MINIMUM_N_IND || t->op == PDLB200_OP_MAXIMUM_N_IND) return launch_nind(t, E);
   return E.fail(PDLB200_EINVAL, "%s is not a reduction", pdlb200_op_name(t->op));
 }
 int pdlb200_matmult(const pdlb200_trans *t, char *err, size_t errlen) {
@@ -218,6 +220,7 @@ int pdlb200_readdata(const pdlb200_trans *t, char *err, size_t errlen) {
   if (op == PDLB200_OP_MATMULT) return launch_matmult(t, E);
   if (op >= PDLB200_OP_PART_SUM && op <= PDLB200_OP_PART_MAX) return launch_partial(t, E);
   if (op >= PDLB200_OP_COLL_SUM && op <= PDLB200_OP_COLL_MAX_IND) return launch_collapse(t, E);
+  if (op == PDLB200_OP_MINIMUM_N_IND || op == PDLB200_OP_MAXIMUM_N_IND) return launch_nind(t, E);
   return E.fail(PDLB200_EINVAL, "pdlb200: op %d has no launcher", op);
 }
 
@@ -229,34 +232,93 @@ struct pdlb200_buf {
   int dev_dirty;  // device copy newer than any host copy
 };
 
+// Raw device allocations behind the store: an exact-size free list in front of the stream-ordered pool.  PDL code
+// creates same-sized temporaries over and over (`$x = $y + $c` makes a fresh 32 MiB output per op): a recycled block
+// costs a hash lookup instead of a cudaMallocAsync + cudaFreeAsync pair (~10 us against a 17 us kernel), and there is
+// no zero-fill (the reference's memset in pdl_allocdata, pdlapi.c:204, is ~75% of its config-1 time).  Reuse is
+// ordered by the launch stream, like the pool itself.
+static std::unordered_multimap<size_t, void *> g_dev_free[16];
+static size_t g_dev_cached[16] = {0};
+static size_t dev_cache_cap() {
+  static size_t cap = 0;
+  if (!cap) { const char *e = getenv("PDLB200_DEV_CACHE_MB"); cap = (size_t)(e ? atoll(e) : 65536) << 20; if (!cap) cap = 1; }
+  return cap;
+}
+void *pdlb200_dev_alloc(size_t nbytes) {
+  if (probe_devices() <= 0) return nullptr;
+  if (!nbytes) nbytes = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_dev_free[dev].find(nbytes);
+    if (it != g_dev_free[dev].end()) {
+      void *p = it->second;
+      g_dev_free[dev].erase(it);
+      g_dev_cached[dev] -= nbytes;
+      return p;
+    }
+  }
+  static bool pool_ready[16] = {false};
+  if (!pool_ready[dev]) {
+    // keep freed blocks in the pool instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    pool_ready[dev] = true;
+  }
+  void *p = nullptr;
+  if (cudaMallocAsync(&p, nbytes, (cudaStream_t)0) != cudaSuccess) {
+    cudaGetLastError();
+    pdlb200_dev_trim();
+    if (cudaMallocAsync(&p, nbytes, (cudaStream_t)0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  return p;
+}
+void pdlb200_dev_free(void *p, size_t nbytes) {
+  if (!p) return;
+  if (!nbytes) nbytes = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 16) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_dev_cached[dev] + nbytes <= dev_cache_cap()) { g_dev_free[dev].emplace(nbytes, p); g_dev_cached[dev] += nbytes; return; }
+  }
+  cudaFreeAsync(p, (cudaStream_t)0);
+}
+void pdlb200_dev_trim(void) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) return;
+  std::unordered_multimap<size_t, void *> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    drop.swap(g_dev_free[dev]);
+    g_dev_cached[dev] = 0;
+  }
+  for (auto &kv : drop) cudaFreeAsync(kv.second, (cudaStream_t)0);
+  cudaStreamSynchronize((cudaStream_t)0);
+}
+
 int pdlb200_buf_new(size_t nbytes, pdlb200_buf **out, char *err, size_t errlen) {
   Err E{err, errlen};
   if (!out) return E.fail(PDLB200_EINVAL, "pdlb200_buf_new: NULL out");
   if (probe_devices() <= 0) return E.fail(PDLB200_ENODEVICE, "pdlb200_buf_new: no CUDA device available");
   pdlb200_buf *b = new pdlb200_buf{nullptr, nbytes, 0, 0};
   cudaGetDevice(&b->device);
-  static bool pool_ready[16] = {false};
-  if (b->device >= 0 && b->device < 16 && !pool_ready[b->device]) {
-    // keep freed blocks in the pool instead of returning them to the driver at every sync
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, b->device) == cudaSuccess) {
-      uint64_t thr = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    pool_ready[b->device] = true;
-  }
   if (nbytes) {
-    // Stream-ordered pool: freed blocks are reused without returning to the driver, and there
-    // is no zero-fill (the reference's memset in pdl_allocdata is ~75% of its config-1 time).
-    cudaError_t e = cudaMallocAsync(&b->dev, nbytes, (cudaStream_t)0);
-    if (e != cudaSuccess) { delete b; return E.fail(PDLB200_ECUDA, "cudaMallocAsync(%zu): %s", nbytes, cudaGetErrorString(e)); }
+    b->dev = pdlb200_dev_alloc(nbytes);
+    if (!b->dev) { delete b; return E.fail(PDLB200_ECUDA, "pdlb200_buf_new: cannot allocate %zu bytes on the device", nbytes); }
   }
   *out = b;
   return PDLB200_OK;
 }
 void pdlb200_buf_free(pdlb200_buf *b) {
   if (!b) return;
-  if (b->dev) cudaFreeAsync(b->dev, (cudaStream_t)0);
+  if (b->dev) pdlb200_dev_free(b->dev, b->nbytes);
   delete b;
 }
 size_t pdlb200_buf_nbytes(const pdlb200_buf *b) { return b ? b->nbytes : 0; }

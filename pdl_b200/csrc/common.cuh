@@ -115,6 +115,7 @@ int launch_reduce(const pdlb200_trans *t, const Err &E);
 int launch_scan(const pdlb200_trans *t, const Err &E);
 int launch_partial(const pdlb200_trans *t, const Err &E);
 int launch_collapse(const pdlb200_trans *t, const Err &E);
+int launch_nind(const pdlb200_trans *t, const Err &E);
 int launch_matmult(const pdlb200_trans *t, const Err &E);
 
 // per-device scratch for two-stage reductions (api.cu); grows, never shrinks

@@ -30,18 +30,64 @@
 #include <mutex>
 #include <unordered_map>
 #include <vector>
+#include <fcntl.h>
 #include <sys/mman.h>
 #include <ucontext.h>
 #include <unistd.h>
 #include "common.cuh"
+
+// The four device-memory primitives the store uses.  PDLB200_STORE_HOSTSIM exists for ONE purpose: tests/ compile this
+// file a second time into a test-only library in which "device" memory is plain malloc'd host memory, so that the
+// dirty-bit / mprotect / fault-handler state machine can be unit-tested on a box without a GPU
+// (tests/test_store_sim.py).  libpdlb200.so is never built with it.
+#ifdef PDLB200_STORE_HOSTSIM
+static int dev_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static void dev_free(void *p) { free(p); }
+static int dev_h2d(void *d, const void *h, size_t n, void *) { memcpy(d, h, n); return 0; }
+static int dev_d2h(void *h, const void *d, size_t n, int) { memcpy(h, d, n); return 0; }
+static void dev_sync() {}
+static int dev_current() { return 0; }
+static void dev_pool_setup() {}
+static const char *dev_err() { return "host simulation"; }
+static int store_device_count() { return 1; }
+namespace pdlb200 { int Err::fail(int code, const char *fmt, ...) const { if (buf && len) snprintf(buf, len, "%s", fmt); return code; } }
+#else
+static int dev_alloc(void **p, size_t n) { if (cudaMallocAsync(p, n, (cudaStream_t)0) == cudaSuccess) return 0; cudaGetLastError(); return 1; }
+static void dev_free(void *p) { cudaFreeAsync(p, (cudaStream_t)0); }   // store buffers are recycled as (mirror, device) PAIRS by the store itself
+static int dev_h2d(void *d, const void *h, size_t n, void *stream) {
+  // pageable source: the call returns once the source has been consumed, so the caller may release / protect it
+  return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)stream) == cudaSuccess ? 0 : 1;
+}
+static int dev_d2h(void *h, const void *d, size_t n, int device) {
+  int cur = 0; cudaGetDevice(&cur);
+  if (cur != device) cudaSetDevice(device);
+  // legacy default stream: ordered after every kernel the binding launched on it
+  const cudaError_t e = cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost);
+  if (cur != device) cudaSetDevice(cur);
+  return e == cudaSuccess ? 0 : 1;
+}
+static void dev_sync() { cudaStreamSynchronize((cudaStream_t)0); }
+static int dev_current() { int d = 0; cudaGetDevice(&d); return d; }
+static void dev_pool_setup() {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev_current()) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+}
+static const char *dev_err() { return cudaGetErrorString(cudaGetLastError()); }
+static int store_device_count() { return pdlb200_device_count(); }
+#endif
 
 namespace pdlb200 {
 namespace {
 
 enum HostState { H0 = 0, HR = 1, HW = 2 };
 
+// The mirror's pages are mapped TWICE from one memfd: `host` is the public mapping the host core sees (its
+// protection carries the host state), `alias` is the store's own always-writable window on the same pages.
+// Downloads land through `alias` while `host` is still PROT_NONE, so a second host thread (autopthread workers)
+// that touches the buffer during the copy faults and waits instead of reading half-arrived data.
 struct MBuf {
-  char *host; void *dev; size_t nbytes, span;   // span = nbytes rounded up to pages (the mmap length)
+  char *host, *alias; void *dev; size_t nbytes, span;   // span = nbytes rounded up to pages (the mmap length)
+  off_t off;                                            // offset of the pages in the arena file
   int hstate; int dev_valid; int device; int refs;
 };
 
@@ -53,6 +99,8 @@ std::atomic<uint64_t> g_stat[8];                 // 0 new 1 recycled 2 uploads 3
 struct sigaction g_old_segv;
 bool g_handler = false;
 size_t g_page = 4096;
+int g_arena_fd = -1;                              // memfd holding every mirror's pages
+off_t g_arena_end = 0;
 
 size_t cache_cap() {
   static size_t cap = 0;
@@ -81,18 +129,11 @@ void protect(MBuf *b, int st) {
 // make the mirror current; for_write -> the host copy becomes the only valid one
 int to_host(MBuf *b, bool for_write) {
   if (b->hstate == H0) {
-    mprotect(b->host, b->span, PROT_READ | PROT_WRITE);
     if (b->dev_valid && b->nbytes) {
-      int cur = 0; cudaGetDevice(&cur);
-      if (cur != b->device) cudaSetDevice(b->device);
-      // legacy default stream: ordered after every kernel the binding launched on it
-      cudaError_t e = cudaMemcpy(b->host, b->dev, b->nbytes, cudaMemcpyDeviceToHost);
-      if (cur != b->device) cudaSetDevice(cur);
-      if (e != cudaSuccess) { mprotect(b->host, b->span, PROT_NONE); return -1; }
+      if (dev_d2h(b->alias, b->dev, b->nbytes, b->device) != 0) return -1;   // public mapping still PROT_NONE
       g_stat[4]++; g_stat[5] += b->nbytes;
     }
-    b->hstate = HW;                             // pages are RW right now
-    if (!for_write) protect(b, HR);
+    protect(b, for_write ? HW : HR);
   }
   if (for_write) { protect(b, HW); b->dev_valid = 0; }
   return 0;
@@ -132,6 +173,13 @@ void install_handler() {
   g_handler = true;
 }
 
+void destroy_buf(MBuf *d) {
+  if (d->dev) dev_free(d->dev);
+  munmap(d->host, d->span); munmap(d->alias, d->span);
+  fallocate(g_arena_fd, FALLOC_FL_PUNCH_HOLE | FALLOC_FL_KEEP_SIZE, d->off, (off_t)d->span);   // give the pages back
+  delete d;
+}
+
 MBuf *alloc_buf(size_t nbytes) {
   {
     auto it = g_free.find(nbytes);
@@ -148,22 +196,27 @@ MBuf *alloc_buf(size_t nbytes) {
   b->nbytes = nbytes;
   b->span = (nbytes + g_page - 1) / g_page * g_page;
   if (!b->span) b->span = g_page;
-  cudaGetDevice(&b->device);
-  void *h = mmap(nullptr, b->span, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-  if (h == MAP_FAILED) { delete b; return nullptr; }
-  b->host = (char *)h;
-  madvise(h, b->span, MADV_HUGEPAGE);            // a later download populates the mirror with 2 MiB pages where THP allows
-  cudaError_t e = cudaMallocAsync(&b->dev, b->span, (cudaStream_t)0);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
+  b->device = dev_current();
+  if (g_arena_fd < 0) g_arena_fd = memfd_create("pdlb200-mirrors", MFD_CLOEXEC);
+  if (g_arena_fd < 0) { delete b; return nullptr; }
+  // 2 MiB-aligned offsets so that huge pages can back large mirrors where shmem THP is enabled
+  const off_t align = b->span >= (2u << 20) ? (off_t)(2u << 20) : (off_t)g_page;
+  b->off = (g_arena_end + align - 1) / align * align;
+  if (ftruncate(g_arena_fd, b->off + (off_t)b->span) != 0) { delete b; return nullptr; }
+  void *h = mmap(nullptr, b->span, PROT_NONE, MAP_SHARED | MAP_NORESERVE, g_arena_fd, b->off);
+  void *al = h == MAP_FAILED ? MAP_FAILED : mmap(nullptr, b->span, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, g_arena_fd, b->off);
+  if (h == MAP_FAILED || al == MAP_FAILED) { if (h != MAP_FAILED) munmap(h, b->span); delete b; return nullptr; }
+  g_arena_end = b->off + (off_t)b->span;
+  b->host = (char *)h; b->alias = (char *)al;
+  madvise(al, b->span, MADV_HUGEPAGE);
+  if (dev_alloc(&b->dev, b->span) != 0) {
     // hand the cached pairs back and retry once
     std::vector<MBuf *> drop;
     for (auto &kv : g_free) drop.push_back(kv.second);
     g_free.clear(); g_cached = 0;
-    for (MBuf *d : drop) { cudaFreeAsync(d->dev, (cudaStream_t)0); munmap(d->host, d->span); delete d; }
-    cudaStreamSynchronize((cudaStream_t)0);
-    e = cudaMallocAsync(&b->dev, b->span, (cudaStream_t)0);
-    if (e != cudaSuccess) { cudaGetLastError(); munmap(h, b->span); delete b; return nullptr; }
+    for (MBuf *d : drop) destroy_buf(d);
+    dev_sync();
+    if (dev_alloc(&b->dev, b->span) != 0) { b->dev = nullptr; destroy_buf(b); return nullptr; }
   }
   g_stat[0]++;
   return b;
@@ -177,15 +230,10 @@ using namespace pdlb200;
 extern "C" {
 
 void *pdlb200_mbuf_new(size_t nbytes) {
-  if (pdlb200_device_count() <= 0) return nullptr;
+  if (store_device_count() <= 0) return nullptr;
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   static bool pool_ready = false;
-  if (!pool_ready) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
-    pool_ready = true;
-  }
+  if (!pool_ready) { dev_pool_setup(); pool_ready = true; }
   MBuf *b = alloc_buf(nbytes);
   if (!b) return nullptr;
   protect(b, H0);
@@ -201,9 +249,7 @@ void *pdlb200_mbuf_adopt(const void *src, size_t nbytes, char *err, size_t errle
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   MBuf *b = find_base(h);
   if (nbytes) {
-    // pageable source: the call returns once the source has been consumed, so the caller may release it
-    cudaError_t e = cudaMemcpyAsync(b->dev, src, nbytes, cudaMemcpyHostToDevice, (cudaStream_t)0);
-    if (e != cudaSuccess) { E.fail(PDLB200_ECUDA, "pdlb200_mbuf_adopt: %s", cudaGetErrorString(e)); pdlb200_mbuf_free(h); return nullptr; }
+    if (dev_h2d(b->dev, src, nbytes, nullptr) != 0) { E.fail(PDLB200_ECUDA, "pdlb200_mbuf_adopt: %s", dev_err()); pdlb200_mbuf_free(h); return nullptr; }
     g_stat[2]++; g_stat[3] += nbytes;
   }
   b->dev_valid = 1;
@@ -221,16 +267,10 @@ void pdlb200_mbuf_free(void *host) {
   MBuf *b = find_base(host);
   if (!b || --b->refs > 0) return;
   g_live.erase((uintptr_t)host);
-  if (b->hstate != H0) {
-    // the mirror was populated by host access: drop the pages so that a recycled buffer starts unpopulated
-    madvise(b->host, b->span, MADV_DONTNEED);
-    protect(b, H0);
-  }
+  protect(b, H0);                                // a recycled buffer starts protected; its pages stay for the next download
   b->dev_valid = 0;
   if (g_cached + b->span <= cache_cap()) { g_free.emplace(b->nbytes, b); g_cached += b->span; return; }
-  cudaFreeAsync(b->dev, (cudaStream_t)0);
-  munmap(b->host, b->span);
-  delete b;
+  destroy_buf(b);
 }
 
 int pdlb200_mbuf_is(const void *host) {
@@ -244,8 +284,7 @@ void *pdlb200_mbuf_dev(void *host, int for_write, int discard, void *stream, cha
   MBuf *b = find_base(host);
   if (!b) { E.fail(PDLB200_EINVAL, "pdlb200_mbuf_dev: %p is not a store buffer", host); return nullptr; }
   if (!b->dev_valid && !discard && b->hstate != H0 && b->nbytes) {
-    cudaError_t e = cudaMemcpyAsync(b->dev, b->host, b->nbytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
-    if (e != cudaSuccess) { E.fail(PDLB200_ECUDA, "pdlb200_mbuf_dev: upload: %s", cudaGetErrorString(e)); return nullptr; }
+    if (dev_h2d(b->dev, b->alias, b->nbytes, stream) != 0) { E.fail(PDLB200_ECUDA, "pdlb200_mbuf_dev: upload: %s", dev_err()); return nullptr; }
     g_stat[2]++; g_stat[3] += b->nbytes;
   }
   b->dev_valid = 1;
@@ -273,6 +312,18 @@ void pdlb200_mbuf_stats(uint64_t *out) {
   for (int i = 0; i < 8; i++) out[i] = g_stat[i].load();
 }
 
+// device-op registry: which transformation vtables of the host core run on the device (the binding registers
+// them at attach time; its make_trans_mutual wrapper asks).  Plain pointers, no host-core types.
+static std::unordered_map<const void *, int> g_devops;
+void pdlb200_devop_register(const void *vtable, int on) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (on) g_devops[vtable] = 1; else g_devops.erase(vtable);
+}
+int pdlb200_devop_is(const void *vtable) {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  return g_devops.count(vtable) != 0;
+}
+
 void pdlb200_mbuf_trim(void) {
   std::vector<MBuf *> drop;
   {
@@ -280,7 +331,7 @@ void pdlb200_mbuf_trim(void) {
     for (auto &kv : g_free) drop.push_back(kv.second);
     g_free.clear(); g_cached = 0;
   }
-  for (MBuf *d : drop) { cudaFreeAsync(d->dev, (cudaStream_t)0); munmap(d->host, d->span); delete d; }
+  for (MBuf *d : drop) destroy_buf(d);
 }
 
 }  // extern "C"

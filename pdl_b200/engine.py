@@ -23,12 +23,21 @@ class PDLError(RuntimeError):
 
 
 class Store:
-    """One device allocation (the reference's pdl.datasv / pdl.data, pdlapi.c:172-209)."""
+    """One device allocation (the reference's pdl.datasv / pdl.data, pdlapi.c:172-209).  `free` (set by the engine
+    that allocated it) hands the block back when the last ndarray that views it goes away."""
 
-    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "__weakref__")
+    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "_free", "__weakref__")
 
-    def __init__(self, engine, handle, ptr, nbytes, keep=None):
-        self.engine, self.handle, self.ptr, self.nbytes, self._keep = engine, handle, ptr, nbytes, keep
+    def __init__(self, engine, handle, ptr, nbytes, keep=None, free=None):
+        self.engine, self.handle, self.ptr, self.nbytes, self._keep, self._free = engine, handle, ptr, nbytes, keep, free
+
+    def __del__(self):
+        f = self._free
+        if f is not None:
+            try:
+                f(self.ptr, self.nbytes)
+            except Exception:  # interpreter shutdown: the library may already be gone
+                pass
 
 
 class Engine:
@@ -70,18 +79,19 @@ class CudaEngine(Engine):
         self._err = C.create_string_buffer(512)
         self._check(self.lib.pdlb200_set_device(device, self._err, 512))
         self.stream = None  # legacy default stream: ordered with torch's default stream
+        self._dev_alloc, self._dev_free = self.lib.pdlb200_dev_alloc, self.lib.pdlb200_dev_free
 
     def _check(self, rc: int) -> None:
         if rc != 0:
             raise PDLError(self._err.value.decode("utf-8", "replace"))
 
     def alloc(self, nbytes: int) -> Store:
-        h = C.c_void_p()
-        self._check(self.lib.pdlb200_buf_new(nbytes, C.byref(h), self._err, 512))
-        ptr = self.lib.pdlb200_buf_devptr(h, 0) or 0
-        st = Store(self, h.value, ptr, nbytes)
-        weakref.finalize(st, self.lib.pdlb200_buf_free, h.value)
-        return st
+        """pdl_allocdata for the device (pdlapi.c:172-209): one C call; recycled blocks come from the exact-size
+        free list in front of the stream-ordered pool, and nothing is zero-filled."""
+        ptr = self._dev_alloc(nbytes)
+        if not ptr:
+            raise PDLError(f"pdl_b200: cannot allocate {nbytes} bytes on the device")
+        return Store(self, None, ptr, nbytes, None, self._dev_free)
 
     def wrap(self, ptr: int, nbytes: int, keep) -> Store:
         """Adopt foreign device memory (e.g. a torch tensor kept alive by `keep`)."""

@@ -55,7 +55,9 @@ _AF = (T.F, T.LD) + T.COMPLEX + (T.D,)
 _STATE_SETBAD = ("setbadif", "setvaltobad")                       # $PDLSTATESETBAD(b), unconditionally
 _STATE_SETGOOD = ("setbadtonan", "setbadtoval", "badmask")        # $PDLSTATESETGOOD(b)
 _STATE_IFFLAG = ("setnantobad", "setinftobad", "setnonfinitetobad",  # if (flag) $PDLSTATESETBAD(b)
-                 "minmaximum")                                       # a row without a usable element (Ufunc.pd:578-583)
+                 "minmaximum",                                       # a row without a usable element (Ufunc.pd:578-583)
+                 "minimum_n_ind", "maximum_n_ind")                   # a slot that could not be filled (Ufunc.pd:531-533)
+_STATE_GOOD_UNLESS_FLAG = ("minimum_n_ind", "maximum_n_ind")         # $PDLSTATESETGOOD(c) first (Ufunc.pd:521)
 
 
 def _bi(name, gentypes, kind="biop"):
@@ -95,6 +97,9 @@ SPECS = {s.name: s for s in [
     OpSpec("minmaximum", [Par("a", ("n",)), Par("cmin", out=True), Par("cmax", out=True),
                           Par("cmin_ind", out=True, typed=T.IND), Par("cmax_ind", out=True, typed=T.IND)], _R, "reduce"),
     OpSpec("magnover", [Par("a", ("n",)), Par("b", out=True)], (T.D, T.LD) + T.COMPLEX + (T.F,), "reduce"),
+    # minimum_n_ind / maximum_n_ind, lib/PDL/Ufunc.pd:502-561: a(n); indx [o]c(m), OtherPars m_size => m
+    OpSpec("minimum_n_ind", [Par("a", ("n",)), Par("c", ("m",), out=True, typed=T.IND)], _R, "nind"),
+    OpSpec("maximum_n_ind", [Par("a", ("n",)), Par("c", ("m",), out=True, typed=T.IND)], _R, "nind"),
     # lib/PDL/Bad.pd:418-480
     _rd("nbadover", _A, T.IND), _rd("ngoodover", _A, T.IND),
     # scans, lib/PDL/Ufunc.pd:120-141 : a(n); [o]b(n)
@@ -130,6 +135,9 @@ SPECS = {s.name: s for s in [
 ]}
 
 
+_SCALARS: dict = {}
+
+
 # ---- scalars -> ndarrays (pdl_SvPDLV + pdl_scalar, lib/PDL/Core/pdlcore.c:64-78) -----------
 
 def as_pdl(x, engine: Engine | None = None) -> PDL:
@@ -137,8 +145,18 @@ def as_pdl(x, engine: Engine | None = None) -> PDL:
         return x
     engine = engine or default_engine()
     if isinstance(x, (bool, int, float, np.integer, np.floating)):
-        t = T.scalar_type(x)
-        return PDL.from_numpy(np.array(x, dtype=T.NP_DTYPE[t]), t, engine)
+        # `$y * 2`: the 0-dim ndarray of a Perl scalar (pdl_scalar, pdlcore.c:64-78).  Uploading 8 bytes costs a
+        # host-device round trip, so the ndarrays of recently used scalars are kept (they are only ever read).
+        key = (id(engine), type(x) is float or isinstance(x, np.floating), x)
+        p = _SCALARS.get(key) if x == x else None
+        if p is None:
+            t = T.scalar_type(x)
+            p = PDL.from_numpy(np.array(x, dtype=T.NP_DTYPE[t]), t, engine)
+            if x == x:
+                if len(_SCALARS) >= 512:
+                    _SCALARS.clear()
+                _SCALARS[key] = p
+        return p._view(p.dims, p.dimincs, p.offs)       # a fresh ndarray object over the same bytes (flags are per object)
     if isinstance(x, (list, tuple, np.ndarray)):
         from .core import pdl
         return pdl(x, engine=engine)
@@ -314,6 +332,70 @@ def _real_inc(p: PDL, j: int) -> int:
     return 0 if (p.ndims <= j or p.dims[j] <= 1) else p.dimincs[j]
 
 
+# ---- descriptor cache: the fast path for repeated shapes (SURVEY.md §7 "launch-latency floor") ---------------
+# Everything run_op derives — type selection, broadcast merging, named dims, output typing, the flag rules — is a
+# function of (op, per-parameter type/dims/strides/flags, OtherPars).  The filled descriptor is kept under that key;
+# a later call with the same key only patches the data pointers, creates the outputs and makes the ONE C-ABI call.
+class _Cached:
+    __slots__ = ("tr", "pars", "nin", "outs", "bval", "force_bad", "name", "ifflag")
+
+    def __init__(self, tr, nin, outs, bval, force_bad, name):
+        self.tr, self.nin, self.outs, self.bval, self.force_bad, self.name = tr, nin, outs, bval, force_bad, name
+        self.pars = [tr.pdls[j] for j in range(tr.npdls)]          # aliases into the descriptor's memory
+        self.ifflag = name in _STATE_IFFLAG
+
+
+_DESC_CACHE: dict = {}
+
+
+def _pkey(p):
+    return None if p is None else (p.datatype, tuple(p.dims), tuple(p.dimincs), p.badflag, p._badvalue)
+
+
+def _cache_key(name, ins, outs, param, goff, sizes):
+    for p in ins:
+        if p._badvalue is not None and p._badvalue != p._badvalue:   # NaN never compares equal: not a usable key
+            return None
+    for p in outs:
+        if p is not None and p._badvalue is not None and p._badvalue != p._badvalue:
+            return None
+    return (name, tuple(_pkey(p) for p in ins), tuple(_pkey(p) for p in outs), param, goff,
+            tuple(sorted(sizes.items())) if sizes else None)
+
+
+def _replay(ent: _Cached, ins: list, outs: list, engine) -> list:
+    pars, nin = ent.pars, ent.nin
+    for j, x in enumerate(ins):
+        par = pars[j]
+        st = x.store
+        par.data = st.ptr if st is not None else None
+        par.offs = x.offs
+    res = []
+    for k, o in enumerate(outs):
+        if o is None:
+            t, dims, incs, nbytes = ent.outs[k]
+            o = PDL(engine, engine.alloc(nbytes), t, dims, incs)
+        par = pars[nin + k]
+        st = o.store
+        par.data = st.ptr if st is not None else None
+        par.offs = o.offs
+        if ent.bval or ent.force_bad:
+            o.badflag = True
+        res.append(o)
+    engine.readdata(ent.tr)
+    name = ent.name
+    if name in _STATE_GOOD_UNLESS_FLAG:
+        for o in res:
+            o.badflag = False
+    if name in _STATE_SETBAD or (ent.ifflag and ent.tr._anybad.value):
+        for o in res:
+            o.badflag = True
+    elif name in _STATE_SETGOOD:
+        for o in res:
+            o.badflag = False
+    return res
+
+
 def prepare_op(name: str, inputs: list, outputs: list | None = None, param: float = 0.0) -> Prepared:
     """Like run_op, but returns a Prepared instead of launching.  Only for calls that need no
     type conversion of inputs or outputs (a single readdata)."""
@@ -321,7 +403,7 @@ def prepare_op(name: str, inputs: list, outputs: list | None = None, param: floa
 
 
 def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool = False, param: float = 0.0,
-           goff: int = 0):
+           goff: int = 0, sizes: dict | None = None):
     """pdl_run_<name>(inputs..., outputs...).  `outputs` entries may be None (null ndarray:
     created with the broadcast dims).  Returns the output ndarrays."""
     spec = SPECS[name]
@@ -336,6 +418,12 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
         if x.isnull():
             raise PDLError(f"PDL::{name}: input parameter is null")
     outs = [None if (o is None or o.isnull()) else o for o in outputs]
+    key = None if _prepare else _cache_key(name, ins, outs, param, goff, sizes)
+    if key is not None:
+        ent = _DESC_CACHE.get(key)
+        if ent is not None:
+            return _replay(ent, ins, outs, engine)
+    ins_given = ins
 
     all_pdls = ins + outs
     transtype = transtype_select(spec, all_pdls)
@@ -351,6 +439,7 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
 
     # named dims (pdl_dim_checks): inputs define them; size-1 stretches; missing dims promote to 1
     ind: dict = dict(spec.fixed)
+    ind.update(sizes or {})         # named dims given as OtherPars (`PDL_Indx m_size => m`)
     for x, par in zip(ins, in_pars):
         for j, dn in enumerate(par.realdims):
             sz = x.dims[j] if j < x.ndims else 1
@@ -411,6 +500,11 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     elif spec.kind == "inner":
         a, b, _c = placeholder
         named = {"ind": [ind["n"]], "rinc": [_real_inc(a, 0), _real_inc(b, 0)]}
+    elif spec.kind == "nind":
+        a, c = placeholder
+        if ind["m"] > ind["n"]:
+            raise PDLError(f"Error in {name}:m_size > n_size")      # RedoDimsCode, Ufunc.pd:518
+        named = {"ind": [ind["n"], ind["m"]], "rinc": [_real_inc(a, 0), _real_inc(c, 0)]}
     elif spec.kind == "part":
         a, rec = placeholder
         named = {"ind": [ind["n"], int(goff)], "rinc": [_real_inc(a, 0), _real_inc(rec, 0)]}
@@ -441,7 +535,19 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
                 o.badflag = False
         return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder,
                         flagged=name in _STATE_IFFLAG)
-    flag = _launch(spec, transtype, placeholder, bc, named, bval)
+    tr = _build_trans(spec, transtype, placeholder, bc, named, bval)
+    engine.readdata(tr)
+    flag = int(tr._anybad.value) if name in _STATE_IFFLAG else 0
+    if key is not None and not temps and all(a is b for a, b in zip(ins, ins_given)):
+        # nothing was converted: the descriptor is reusable for every later call with the same key
+        if len(_DESC_CACHE) >= 4096:
+            _DESC_CACHE.clear()
+        force_bad = spec.kind == "reduce" and ind.get("n") == 0 and name in ("minimum", "maximum", "minimum_ind", "maximum_ind")
+        meta = [(o.datatype, list(o.dims), list(o.dimincs), o.nelem * T.SIZE[o.datatype]) for o in placeholder[len(ins):]]
+        _DESC_CACHE[key] = _Cached(tr, len(ins), meta, bval, force_bad, name)
+    if name in _STATE_GOOD_UNLESS_FLAG:
+        for o in placeholder[len(ins):]:
+            o.badflag = False
     if name in _STATE_SETBAD or (name in _STATE_IFFLAG and flag):
         for o in placeholder[len(ins):]:
             o.badflag = True

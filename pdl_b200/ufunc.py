@@ -59,10 +59,29 @@ def minmaximum(a, cmin=None, cmax=None, cmin_ind=None, cmax_ind=None):
 minmaxover = minmaximum
 
 
+def _mk_n_ind(name):
+    def f(a, c=None, m_size=None):
+        """PDL::%s(a(n); indx [o]c(m); m_size) — lib/PDL/Ufunc.pd:502-561: `c` may be the size (as in the
+        reference's Perl wrapper), an existing output, or None with m_size."""
+        a = as_pdl(a)
+        if c is not None and not hasattr(c, "dims"):
+            c, m_size = None, int(c)
+        if m_size is None:
+            m_size = c.dims[0]
+        return run_op(name, [a], [c], sizes={"m": int(m_size)})[0]
+    f.__name__ = name
+    return f
+
+
+minimum_n_ind = _mk_n_ind("minimum_n_ind")
+maximum_n_ind = _mk_n_ind("maximum_n_ind")
+min_n_ind, max_n_ind = minimum_n_ind, maximum_n_ind
+
+
 def minmax(a):
     """PDL::minmax (Ufunc.pd:738): map $_->sclr, ($x->flat->minmaximum)[0,1]"""
     r = minmaximum(as_pdl(a).flat())
     return r[0].sclr(), r[1].sclr()
 
 
-__all__ = ["minmaximum", "minmaxover", "minmax"] + _REDUCERS + list(_WHOLE) + ["avgover", "davgover", "minover", "maxover", "minover_ind", "maxover_ind"]
+__all__ = ["minmaximum", "minmaxover", "minmax", "minimum_n_ind", "maximum_n_ind"] + _REDUCERS + list(_WHOLE) + ["avgover", "davgover", "minover", "maxover", "minover_ind", "maxover_ind"]

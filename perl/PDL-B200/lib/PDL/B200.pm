@@ -11,7 +11,7 @@ package PDL::B200;
 # PDL::Primitive shared objects and swap the readdata/redodims pointers (B200.xs).
 use strict; use warnings;
 use PDL::Core ();
-use PDL::Ops (); use PDL::Ufunc (); use PDL::Primitive (); use PDL::Bad ();
+use PDL::Ops (); use PDL::Ufunc (); use PDL::Primitive (); use PDL::Bad (); use PDL::Slices ();
 require DynaLoader;
 our @ISA = ('DynaLoader');
 our $VERSION = '0.01';
@@ -27,11 +27,18 @@ our %OPS = (
     minimum=>36, maximum=>37, minimum_ind=>38, maximum_ind=>39, andover=>40, orover=>41,
     bandover=>42, borover=>43, zcover=>44, xorover=>45, bxorover=>46,
     cumusumover=>50, cumuprodover=>51, dcumusumover=>52, dcumuprodover=>53,
-    minmaximum=>77, magnover=>78 },
+    minmaximum=>77, magnover=>78, minimum_n_ind=>90, maximum_n_ind=>91 },
   'PDL::Bad' => { nbadover=>47, ngoodover=>48, isbad=>63, isgood=>64, isnan=>65, setbadif=>66, setvaltobad=>67,
     setnantobad=>68, setinftobad=>69, setnonfinitetobad=>70, setbadtonan=>71, setbadtoval=>72, badmask=>73,
     copybad=>74 },
   'PDL::Primitive' => { matmult=>60, axisvalues=>75, inner=>76, outer=>79 },
+);
+
+# flat parent -> child transformations either side of device ops: converttypei (`float_nd + 1.5`) and _clump_int
+# (`$x->sum` = flat->sumover); value = [PDLB200_OP_*, kind]
+our %FLAT = (
+  'PDL::Core'   => { converttypei => [61, 1] },
+  'PDL::Slices' => { _clump_int   => [28, 2] },
 );
 
 sub _libref {
@@ -55,7 +62,47 @@ sub attach {
       $ATTACHED{$op} = 1;
     }
   }
+  for my $module (sort keys %FLAT) {
+    my $lib = _libref($module);
+    for my $op (sort keys %{ $FLAT{$module} }) {
+      next if %only && !$only{$op};
+      my $addr = DynaLoader::dl_find_symbol($lib, "pdl_${op}_vtable")
+        or die "PDL::B200: pdl_${op}_vtable not found in $module";
+      _hook($addr, @{ $FLAT{$module}{$op} });
+      $ATTACHED{$op} = 1;
+    }
+  }
+  _wrap_perl_side() unless %only;
   return scalar keys %ATTACHED;
+}
+
+# Perl-level entry points that refuse or bypass PDL_DONTTOUCHDATA ndarrays: hand the data back to a plain SV
+# first (get_dataref: lib/PDL/Core.xs:1145-1160; setdims / reshape: pdlapi.c:183 via pdl_allocdata).
+our %WRAPPED;
+sub _wrap_perl_side {
+  no strict 'refs'; no warnings 'redefine';
+  for my $name (qw(get_dataref setdims reshape set_datatype upd_data)) {
+    next if $WRAPPED{$name};
+    my $orig = \&{"PDL::$name"};
+    $WRAPPED{$name} = $orig;
+    *{"PDL::$name"} = sub { PDL::B200::to_host($_[0]) if ref $_[0] && !$_[0]->isnull; goto &$orig; };
+  }
+  # `($a->flowing * $b)->sumover`: the deferred product and the reduction run as ONE launch (inner)
+  if (!$WRAPPED{sumover}) {
+    my $orig = \&PDL::sumover;
+    $WRAPPED{sumover} = $orig;
+    *PDL::sumover = sub {
+      if (@_ == 1 && ref $_[0] && (my @p = PDL::B200::_pending_product($_[0]))) {
+        $_ = $_->getndims ? $_ : $_->dummy(0) for @p;
+        return PDL::inner(@p);
+      }
+      goto &$orig;
+    };
+  }
+}
+sub _unwrap_perl_side {
+  no strict 'refs'; no warnings 'redefine';
+  *{"PDL::$_"} = delete $WRAPPED{$_} for keys %WRAPPED;
 }
 
 sub import {
@@ -64,6 +111,6 @@ sub import {
   attach() unless %ATTACHED;
 }
 
-END { detach() }
+END { _unwrap_perl_side(); detach() }
 
 1;

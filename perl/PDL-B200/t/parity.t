@@ -86,7 +86,20 @@ for my $t (@types) {
   both("magnover $t",     sub { ($a % 5)->magnover });
   both("outer $t",        sub { outer($a->slice(':,(1)') % 9, $b->slice('0:40,(2)') % 9) });
   both("outer bad $t",    sub { outer($bad->slice(':,(0)') % 9, $b->slice('0:40,(2)') % 9) });
+  both("minimum_n_ind $t",     sub { $a->minimum_n_ind(4) });
+  both("maximum_n_ind bad $t", sub { $bad->maximum_n_ind(3) });
+  both("maximum_n_ind short $t", sub { $bad->slice('0:1,:')->maximum_n_ind(2) });     # all-BAD rows: BAD slots + badflag
+  both("abs2 $t",         sub { ($a % 11)->abs2 });
+  both("convert $t -> float", sub { $a->float });
+  both("convert bad $t -> long", sub { $bad->long });
+  both("flat sum $t",     sub { ($a % 5)->sum + pdl(0) });
+  both("ipow $t", sub { ($a % 3)->ipow(3) }) if !$t->integer || $t == longlong;
   if (!$t->integer) {
+    { # libm vs CUDA math library: transcendentals agree within a few ulp, not bit for bit
+      my $arg = (abs($a) % 9) + 1;
+      PDL::B200::enable(1); my $g = $arg->log10; PDL::B200::enable(0); my $c = $arg->log10; PDL::B200::enable(1);
+      ok(all(abs($g - $c) <= 4e-7 * abs($c) + 1e-30), "log10 $t within tolerance of the CPU path");
+    }
     my $sp = $a->copy; $sp->set(3, 1, 'nan'); $sp->set(4, 2, 'inf');
     both("setnantobad $t",       sub { $sp->setnantobad });
     both("setnantobad clean $t", sub { $a->setnantobad });
@@ -96,14 +109,14 @@ for my $t (@types) {
     both("isnan $t",             sub { $sp->isnan });
   }
 }
-# large: exercises the managed-memory path (outputs created managed, inputs migrated on first use)
+# large: exercises the device store (outputs created in it, inputs adopted on first use)
 {
   my $y = sequence(2048, 2048); my $c = sequence(2048, 2048) * 0.5 + 1;
   both("cfg1 2048x2048 double", sub { $y + $c });
   both("chained, stays on device", sub { (($y + $c) * 2 - $y)->sumover });   # every value exactly representable
   my $x = $y + $c;
-  ok(PDL::B200::ptr_kind($x) == 2, 'op output lives in managed memory');
-  ok(PDL::B200::ptr_kind($y) == 2, 'large input was migrated to managed memory');
+  is(PDL::B200::store_state($x), 4, 'op output lives in the device store (device copy current, host mirror not populated)');
+  ok(PDL::B200::store_state($y) >= 4, 'large input was adopted into the device store');
   is($x->at(5, 7), $y->at(5, 7) + $c->at(5, 7), 'host read of a device result (lazy sync)');
   $x->set(0, 0, 42); my $z = $x + 1;
   is($z->at(0, 0), 43, 'host write then device op sees the new value');

@@ -129,6 +129,9 @@ sub add_case {
       $out = PDL::outer($args[0], $args[1]);
     } elsif ($kind eq 'minmaximum') {   # four outputs
       $out = [ $args[0]->minmaximum ];
+    } elsif ($kind eq 'n_ind') {        # minimum_n_ind / maximum_n_ind with the size given
+      my $m = $call->{op};
+      $out = $args[0]->$m($call->{m});
     } else { die "kind $kind" }
     1;
   };
@@ -508,3 +511,30 @@ flush_cases('outer.json');
   add_case("edge-cumuprodover-bad-first", [[with_bad(mk('double',[9,2],'small'), 0, 9)]], {kind=>'reduce', op=>'cumuprodover'}, 0);
 }
 flush_cases('edge.json');
+
+# ---------------------------------------------------------------- round 2: minimum_n_ind / maximum_n_ind (Ufunc.pd:502-561),
+# inner / magnover with non-finite values and overflow (Primitive.pd:48-70, Ufunc.pd:1235-1256)
+for my $t (@TYPES) {
+  for my $op (qw(minimum_n_ind maximum_n_ind)) {
+    add_case("$op-$t", [[mk($t,[13,4],'small')]], {kind=>'n_ind', op=>$op, m=>3});
+    add_case("$op-$t-all", [[mk($t,[6,2],'mixed')]], {kind=>'n_ind', op=>$op, m=>6});
+    add_case("$op-$t-long", [[mk($t,[3000],'mixed')]], {kind=>'n_ind', op=>$op, m=>4});
+    add_case("$op-$t-strided", [[mk($t,[24,3],'small'), [['slice','-1:0:-2,:']]]], {kind=>'n_ind', op=>$op, m=>5});
+    # rows 1 and 2 cannot fill their slots, the LAST row can: the output ends up with BAD values and badflag 0
+    add_case("$op-$t-bad-early-row", [[with_bad(mk($t,[5,4],'small'), 5..9, 10, 11, 12, 14)]], {kind=>'n_ind', op=>$op, m=>2});
+    # the last row cannot: badflag 1
+    add_case("$op-$t-bad-last-row", [[with_bad(mk($t,[5,4],'small'), 2, 15, 16, 17, 19)]], {kind=>'n_ind', op=>$op, m=>2});
+    add_case("$op-$t-ties", [[pdl($TOBJ{$t}, [[3,1,1,3,2],[5,5,5,5,5]])]], {kind=>'n_ind', op=>$op, m=>4});
+  }
+}
+for my $t (qw(float double)) {
+  my $rows = pdl($TOBJ{$t}, [[$NAN,1,2,0],[1,$NAN,2,$NAN],[$NAN,$NAN,$NAN,$NAN],[0,-0.0,0,-0.0],[$INF,-$INF,5,$NAN]]);
+  add_case("$_-$t-nan-zero", [[$rows]], {kind=>'n_ind', op=>$_, m=>3}) for qw(minimum_n_ind maximum_n_ind);
+  my $big = $t eq 'float' ? 3e38 : 1e308;
+  my $nf = pdl($TOBJ{$t}, [[1,$INF,2,3],[$big,$big,$big,1],[$INF,-$INF,1,1],[-$INF,5,1,1],[$NAN,1,2,3],[1,2,3,4]]);
+  my $two = pdl($TOBJ{$t}, 2);
+  add_case("inner-$t-nonfinite", [[$nf],[$two]], {kind=>'inner'}, 0);
+  add_case("magnover-$t-nonfinite", [[$nf]], {kind=>'reduce', op=>'magnover'}, 0);
+}
+add_case("minimum_n_ind-too-many", [[mk('double',[3],'small')]], {kind=>'n_ind', op=>'minimum_n_ind', m=>4});
+flush_cases('round2.json');

@@ -74,6 +74,8 @@ def run_call(call, args):
         return P.outer(args[0], args[1])
     if kind == "minmaximum":
         return list(ufunc.minmaximum(args[0]))
+    if kind == "n_ind":
+        return getattr(ufunc, call["op"])(args[0], call["m"])
     raise ValueError(kind)
 
 
@@ -106,7 +108,8 @@ def check_case(case, engine):
         except PDLError as e:
             want = case["error"]
             key = ("Mismatched implicit broadcast dimension" if "Mismatched" in want else
-                   "index 'n' size 3, but ndarray dim has size 4" if "index 'n'" in want else "Dim mismatch in matmult")
+                   "index 'n' size 3, but ndarray dim has size 4" if "index 'n'" in want else
+                   "m_size > n_size" if "m_size > n_size" in want else "Dim mismatch in matmult")
             assert key in str(e), (str(e), want)
             if "Dim mismatch" in want:
                 assert str(e).strip() == want.strip()
