@@ -69,6 +69,38 @@ __device__ __forceinline__ TO ew_apply(const EwPlan &p, TI a, TB b, TI abad, TB 
     return (ba || bb) ? cbad : r;
   }
 }
+// ---- SIMD-within-a-register forms for 8/16-bit integer types -------------------------------------------------
+// A 16-byte unit holds 16 (8) elements: per-element code costs 5-7 issue slots per element (extract, compare with
+// the badvalue twice, op, select, insert), which makes these types issue-bound far below the HBM roofline in BAD
+// mode.  Here the BAD test and the merge with the output badvalue are done on whole 32-bit words (the exact
+// zero-lane test on `w ^ badword`), and ops that have a lane-wise word form (`Op::kPackedWords` + `fw<T>(a, b)`)
+// never unpack at all.  Bit-exact: wrapping integer arithmetic lane by lane.
+template <class Op, class = void> struct op_packed : std::false_type {};
+template <class Op> struct op_packed<Op, std::void_t<decltype(Op::kPackedWords)>> : std::true_type {};
+
+// float/double ops that evaluate a whole unit at once (`Op::kPackFloat` + `fpack<T, VEC>(a, b, c)`, ew_ops.cuh)
+template <class Op, class = void> struct op_packfloat : std::false_type {};
+template <class Op> struct op_packfloat<Op, std::void_t<decltype(Op::kPackFloat)>> : std::true_type {};
+
+// ops whose body needs more than the 64 registers of the 4-CTAs/SM configuration (`Op::kHeavy`): 3 CTAs/SM, 80 registers
+template <class Op, class = void> struct op_heavy : std::false_type {};
+template <class Op> struct op_heavy<Op, std::void_t<decltype(Op::kHeavy)>> : std::true_type {};
+
+template <class T> __device__ __forceinline__ uint32_t ew_splat(T v) {
+  if constexpr (sizeof(T) == 1) return 0x01010101u * (uint32_t)(uint8_t)v; else return 0x00010001u * (uint32_t)(uint16_t)v;
+}
+// all-ones in every lane of w that equals the same lane of badw
+template <class T> __device__ __forceinline__ uint32_t ew_eq_lanes(uint32_t w, uint32_t badw) {
+  const uint32_t x = w ^ badw;
+  if constexpr (sizeof(T) == 1) {
+    const uint32_t hi = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;   // 0x80 in each zero byte, exact
+    return (hi >> 7) * 0xffu;
+  } else {
+    const uint32_t hi = ~(((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u;
+    return (hi >> 15) * 0xffffu;
+  }
+}
+
 template <class Op> __device__ __forceinline__ void ew_publish_flag(const EwPlan &p, int flag) {
   if constexpr (op_badaware<Op>::value) { if (flag && p.flag) atomicOr(p.flag, 1); }
 }
@@ -202,11 +234,48 @@ template <class Op, class TI, class TO, bool BAD, int NIN, int VEC, class TB>
 __device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI> &ra, const Pack<TB> &rb, TO *dst, int64_t sc0,
                                                  int cnt, TI abad, TB bbad, TO cbad, int &flag) {
   Pack<TO> rc;
+  constexpr bool kSwar = tt<TI>::is_int && sizeof(TI) <= 2 && std::is_same<TI, TO>::value && std::is_same<TI, TB>::value &&
+                         !op_badaware<Op>::value && (BAD || op_packed<Op>::value);
+  if constexpr (kSwar) {
+    const uint32_t aw[4] = {ra.q.x, ra.q.y, ra.q.z, ra.q.w};
+    const uint32_t bw[4] = {rb.q.x, rb.q.y, rb.q.z, rb.q.w};
+    uint32_t cw[4];
+    if constexpr (op_packed<Op>::value) {
 #pragma unroll
-  for (int k = 0; k < VEC; k++) {
-    const TI a = ra.e[k];
-    const TB b = (NIN > 1) ? rb.e[k] : TB(0);
-    rc.e[k] = ew_apply<Op, TI, TB, TO, BAD, NIN>(p, a, b, abad, bbad, cbad, flag);
+      for (int i = 0; i < 4; i++) cw[i] = Op::template fw<TI>(aw[i], (NIN > 1) ? bw[i] : 0u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; k++) rc.e[k] = Op::template f<TI, TO>(ra.e[k], (NIN > 1) ? rb.e[k] : TB(0));
+      cw[0] = rc.q.x; cw[1] = rc.q.y; cw[2] = rc.q.z; cw[3] = rc.q.w;
+    }
+    if constexpr (BAD) {
+      const uint32_t abw = ew_splat<TI>(abad), bbw = ew_splat<TB>(bbad), cbw = ew_splat<TO>(cbad);
+      const uint32_t ca = p.badchk[0] ? 0xffffffffu : 0u, cb = (NIN > 1 && p.badchk[1]) ? 0xffffffffu : 0u;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        uint32_t m = ew_eq_lanes<TI>(aw[i], abw) & ca;
+        if (NIN > 1) m |= ew_eq_lanes<TB>(bw[i], bbw) & cb;
+        cw[i] = (cw[i] & ~m) | (cbw & m);
+      }
+    }
+    rc.q = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+  } else if constexpr (op_packfloat<Op>::value && !tt<TI>::is_int && std::is_same<TI, TO>::value && std::is_same<TI, TB>::value) {
+    Op::template fpack<TI, VEC>(ra, rb, rc);
+    if constexpr (BAD) {
+#pragma unroll
+      for (int k = 0; k < VEC; k++) {
+        bool bad = p.badchk[0] && is_bad(ra.e[k], abad, p.badnan[0] != 0);
+        if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(rb.e[k], bbad, p.badnan[1] != 0));
+        rc.e[k] = bad ? cbad : rc.e[k];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; k++) {
+      const TI a = ra.e[k];
+      const TB b = (NIN > 1) ? rb.e[k] : TB(0);
+      rc.e[k] = ew_apply<Op, TI, TB, TO, BAD, NIN>(p, a, b, abad, bbad, cbad, flag);
+    }
   }
   ew_store<TO, VEC>(rc, reinterpret_cast<char *>(dst), 0, sc0, p.vec[NIN], cnt);
 }
@@ -214,7 +283,7 @@ __device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI>
 // 64 registers (4 CTAs/SM) for the good-mode bodies; the BAD bodies carry the extra compares/selects and
 // get 80 (3 CTAs/SM) rather than spilling inside the hot loop.
 template <class Op, class TI, class TO, bool BAD, int NIN, int UNROLL, class TB = TI>
-__global__ void __launch_bounds__(EW_THREADS, BAD ? 3 : 4)
+__global__ void __launch_bounds__(EW_THREADS, (BAD || op_heavy<Op>::value) ? 3 : 4)
 ew_tile_kernel(const __grid_constant__ EwPlan p) {
   constexpr int VEC = ew_vec<TI, TO, TB>();
   constexpr int64_t TILE = (int64_t)EW_THREADS * UNROLL * VEC;

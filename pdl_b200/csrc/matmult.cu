@@ -179,7 +179,9 @@ int launch_matmult(const pdlb200_trans *t, const Err &E) {
   const char *force = getenv("PDLB200_MATMULT");  // "exact" | "dmma" (default: dmma when eligible)
   const bool want_exact = force && !strcmp(force, "exact");
   if (t->datatype == PDLB200_D && !t->bvalflag && !want_exact) {
-    int rc = launch_matmult_dmma(t, p, E);
+    int rc = launch_matmult_tma(t, p, E);         // TMA-staged tiles when the layout allows
+    if (rc != PDLB200_EUNSUPPORTED) return rc;
+    rc = launch_matmult_dmma(t, p, E);
     if (rc != PDLB200_EUNSUPPORTED) return rc;  // shape not eligible -> exact kernel
   }
   switch (t->datatype) {

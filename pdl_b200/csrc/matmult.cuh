@@ -20,5 +20,6 @@ struct MmPlan {
 };
 
 int launch_matmult_dmma(const pdlb200_trans *t, const MmPlan &p, const Err &E);  // matmult_dmma.cu
+int launch_matmult_tma(const pdlb200_trans *t, const MmPlan &p, const Err &E);   // matmult_tma.cu
 
 }  // namespace pdlb200

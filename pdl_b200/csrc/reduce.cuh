@@ -157,6 +157,24 @@ template <class T, class O> struct RProd {
     x.s = wrap_mul<O>(x.s, (O)v); x.any = 1;
     if constexpr (kPrefix) { if ((O)v == O(0) && rel < x.z) x.z = rel; }
   }
+  // 8/16-bit integers into a 32-bit product: BAD lanes are replaced by 1 on whole words (no per-element compare /
+  // branch), then one multiply per lane
+  static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2 && std::is_same<O, int32_t>::value;
+  template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
+    const uint32_t badw = swar_splat<T>(abad), onew = swar_splat<T>(T(1));
+    const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
+    int32_t nbad = 0;
+    uint32_t s = (uint32_t)x.s;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t g = w[i];
+      if constexpr (BADK == 1) { const uint32_t m = swar_eq_mask<T>(g, badw, nbad); g = (g & ~m) | (onew & m); }
+#pragma unroll
+      for (int k = 0; k < (int)(4 / sizeof(T)); k++) s *= (uint32_t)(int32_t)(T)(g >> (8 * sizeof(T) * k));
+    }
+    x.s = (O)s;
+    x.any |= (nbad != (int32_t)(16 / sizeof(T)));
+  }
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t lo) {
     Acc x; x.s = l.s; x.any = l.any; x.pad = 0; x.z = (l.z == 0x7fffffff) ? RD_NOIDX : lo + l.z; return x;
   }
@@ -349,6 +367,20 @@ template <class T, bool ISMAX> struct RMinMaxInt {
   }
 };
 
+// minimum_ind / maximum_ind of 8/16-bit integer rows in TWO phases: the packed value reduction above (one
+// VIMNMX-class instruction per word), then a search for the FIRST element equal to the extreme (one packed
+// equality test per word, the row comes back from L1/L2).  Integers have no NaN and no -0, so "first index of the
+// extreme value" is exactly the reference's strict-compare rule (Ufunc.pd:481-491).  kFindFirst makes the kernel
+// run phase 2; rows that are cut into chunks (nchunks > 1) use the per-element reducer instead.
+template <class T, bool ISMAX> struct RMinMaxIntInd : RMinMaxInt<T, ISMAX> {
+  static constexpr bool kFindFirst = true;
+  using Acc = typename RMinMaxInt<T, ISMAX>::Acc;
+  // only reached by the (never launched) chunked instantiations: the index comes from phase 2 in the row kernel
+  static __device__ __forceinline__ void finish(const Acc &, const RdPlan &p, int64_t *out) { *out = from_bits<int64_t>(p.bbad); }
+};
+template <class R, class = void> struct rd_kfind { static constexpr bool value = false; };
+template <class R> struct rd_kfind<R, std::void_t<decltype(R::kFindFirst)>> { static constexpr bool value = R::kFindFirst; };
+
 // andover orover zcover xorover (logical) and bandover borover bxorover (bitwise), Ufunc.pd:143-187.
 // KIND: 0 and, 1 or, 2 zc, 3 xor, 4 band, 5 bor, 6 bxor.  Output type == input type.
 template <class T, int KIND> struct RBits {
@@ -512,6 +544,84 @@ __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64
          else rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad); }
 }
 
+// Phase 2 of the two-phase _ind reducers: a candidate for the smallest index in [0, n) with row[i] == e, such that
+// the minimum of the candidates over the cooperating group IS that index (RD_NOIDX: this thread has none).
+// Each warp of the group scans its own contiguous share of the row front to back, 32 vectors at a time, and
+// stops at the first wavefront that contains a hit (`__any_sync`): with ties (the usual case for small integer
+// types) the scan ends after a few hundred bytes; without them the row is re-read once from L1/L2.
+template <class T>
+__device__ __forceinline__ int64_t rd_first_eq(const T *row, int64_t n, int64_t inc, int lane, int width, T e) {
+  constexpr int VEC = 16 / sizeof(T);
+  if (width == 1) {                               // thread per row: plain sequential search
+    for (int64_t i = 0; i < n; i++) if (row[i * inc] == e) return i;
+    return RD_NOIDX;
+  }
+  const int nw = width >> 5, wid = lane >> 5, l = lane & 31;
+  int64_t best = RD_NOIDX;
+  if (inc == 1) {
+    const uintptr_t addr = (uintptr_t)row;
+    int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / sizeof(T));
+    if (head > n) head = n;
+    if (wid == 0 && l < head && row[l] == e) best = l;                     // head < 16 elements
+    const int64_t nv = (n - head) / VEC;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(row + head);
+    const uint32_t ew = swar_splat<T>(e);
+    const int64_t per = (nv + nw - 1) / nw;
+    const int64_t j1 = (wid + 1) * per < nv ? (wid + 1) * per : nv;
+    for (int64_t j0 = wid * per; j0 < j1; j0 += 32) {
+      const int64_t j = j0 + l;
+      int64_t cand = RD_NOIDX;
+      if (j < j1) {
+        const uint4 q = vp[j];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        int32_t dummy = 0;
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {
+          const uint32_t m = swar_eq_mask<T>(w[i], ew, dummy);
+          if (m) cand = head + j * VEC + i * (int)(4 / sizeof(T)) + (__ffs(m) - 1) / (int)(8 * sizeof(T));
+        }
+      }
+      if (__any_sync(0xffffffffu, cand != RD_NOIDX)) { best = cand < best ? cand : best; break; }
+    }
+    if (wid == nw - 1) {                                                   // tail < VEC elements
+      const int64_t i = head + nv * VEC + l;
+      if (i < n && row[i] == e && i < best) best = i;
+    }
+  } else {
+    const int64_t per = (n + nw - 1) / nw;
+    const int64_t i1 = (wid + 1) * per < n ? (wid + 1) * per : n;
+    for (int64_t i0 = wid * per; i0 < i1; i0 += 32) {
+      const int64_t i = i0 + l;
+      const bool hit = i < i1 && row[i * inc] == e;
+      if (__any_sync(0xffffffffu, hit)) { if (hit) best = i; break; }
+    }
+  }
+  return best;
+}
+// minimum of an int64 over the cooperating group (MODE as in rd_group_reduce); smem: RD_THREADS/32 + 1 slots
+template <int MODE>
+__device__ __forceinline__ int64_t rd_group_min64(int64_t v, int64_t *smem) {
+  if (MODE >= 1) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { const int64_t o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+  }
+  if (MODE == 2) {
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      v = (threadIdx.x < RD_THREADS / 32) ? smem[threadIdx.x] : RD_NOIDX;
+#pragma unroll
+      for (int m = (RD_THREADS / 64); m >= 1; m >>= 1) { const int64_t o = __shfl_xor_sync(0xffffffffu, v, m); v = o < v ? o : v; }
+      if (threadIdx.x == 0) smem[RD_THREADS / 32] = v;
+    }
+    __syncthreads();
+    v = smem[RD_THREADS / 32];
+    __syncthreads();
+  }
+  return v;
+}
+
 __device__ __forceinline__ void rd_row_offsets(const RdPlan &p, int64_t row, int64_t &oa, int64_t &ob) {
   oa = 0; ob = 0;
   for (int d = 0; d < p.nd; d++) {
@@ -604,6 +714,14 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
     const bool writer = (MODE == 0) || (MODE == 1 && lane == 0) || (MODE == 2 && threadIdx.x == 0);
     if (p.nchunks == 1) {
       O *out = reinterpret_cast<O *>(p.b) + ob;
+      if constexpr (rd_kfind<R>::value) {   // two-phase _ind: acc holds the row's extreme VALUE, every thread has it
+        static_assert(sizeof(Acc) >= sizeof(int64_t), "smem slots are reused for the index reduction");
+        int64_t first = RD_NOIDX;
+        if (acc.any) first = rd_first_eq<T>(rp, p.n, p.inc_n, lane, width, acc.cur);
+        first = rd_group_min64<MODE>(first, reinterpret_cast<int64_t *>(smem));
+        if (writer) *out = acc.any ? (O)first : from_bits<O>(p.bbad);
+        continue;
+      }
       if constexpr (R::kPrefix) {
         if (acc.z != RD_NOIDX) {   // uniform over the group: every thread holds the total
           const O v = rd_prod_prefix<R, T, O, BAD, MODE>(rp, acc.z, p.inc_n, lane, width, abad, abadnan, smem);

@@ -1,4 +1,5 @@
 // reduce_minmax_ind.cu — minimum_ind maximum_ind (lib/PDL/Ufunc.pd:477-500).
+#include <cstdlib>
 #include "reduce.cuh"
 namespace pdlb200 {
 #define MM_CASES(ISMAX, WANT, NAME) \
@@ -14,6 +15,14 @@ namespace pdlb200 {
   case PDLB200_D:   return mm<double,   ISMAX, WANT>(t, NAME, E);
 template <class T, bool ISMAX, bool WANT>
 static int mm(const pdlb200_trans *t, const char *name, const Err &E) {
+  if constexpr (WANT && sizeof(T) <= 2) {
+    // 8/16-bit rows: packed value reduction + first-index search (two phases) unless the rows are cut into chunks
+    RdPlan p; RdLaunch l;
+    const int rc = rd_build_plan(t, sizeof(T), sizeof(int64_t), sizeof(typename RMinMaxIntInd<T, ISMAX>::Acc), &p, &l, E);
+    if (rc) return rc;
+    if (p.nchunks == 1 && !getenv("PDLB200_IND_PER_ELEMENT"))
+      return rd_launch_typed<RMinMaxIntInd<T, ISMAX>, T, int64_t>(t, name, E);
+  }
   if constexpr (WANT) return rd_launch_typed<RMinMax<T, int64_t, ISMAX, true>, T, int64_t>(t, name, E);
   else if constexpr (tt<T>::is_int) return rd_launch_typed<RMinMaxInt<T, ISMAX>, T, T>(t, name, E);
   else return rd_launch_typed<RMinMax<T, T, ISMAX, false>, T, T>(t, name, E);

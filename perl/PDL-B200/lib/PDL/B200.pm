@@ -81,7 +81,7 @@ sub attach {
 our %WRAPPED;
 sub _wrap_perl_side {
   no strict 'refs'; no warnings 'redefine';
-  for my $name (qw(get_dataref setdims reshape set_datatype upd_data)) {
+  for my $name (qw(get_dataref setdims reshape set_datatype upd_data datasv_refcount)) {
     next if $WRAPPED{$name};
     my $orig = \&{"PDL::$name"};
     $WRAPPED{$name} = $orig;

@@ -135,8 +135,8 @@ def check_case(case, engine):
     tol = case.get("tol_ulp")
     # float sum/product/average: a NaN result is NaN on both sides, but its sign/payload is an
     # artefact of summation order and of x86-vs-GPU NaN generation, not of PDL semantics
-    nan_free = case["call"]["kind"] in ("reduce", "whole") and any(
-        k in case["call"]["op"] for k in ("sum", "prod", "aver", "avg"))
+    nan_free = (case["call"]["kind"] in ("reduce", "whole") and any(
+        k in case["call"]["op"] for k in ("sum", "prod", "aver", "avg", "magn"))) or case["call"]["kind"] == "inner"
     if dt.kind == "f" and (tol or nan_free):
         tol = tol or 0
         d = ulp_diff(got, exp)

@@ -249,6 +249,92 @@ def test_matmult_default_path_double(engines):
     assert np.all(np.abs(g - wnt) <= bound)
 
 
+@pytest.mark.parametrize("shape", [(128, 16, 128), (384, 1000, 256), (130, 17, 129), (257, 50, 131), (1024, 8, 1024), (128, 1, 128)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_matmult_tma_tiles_edges_and_views(engines, shape):
+    """The TMA-staged DMMA kernel (matmult_tma.cu): full tiles, ragged edges in every dim (the hardware zero-fills
+    the out-of-range part of a box), and operands that are windows into bigger ndarrays (row pitch != row length).
+    Exactly representable inputs -> bit-exact whatever the k order inside a k-tile."""
+    cuda = engines[0]
+    h, tt, w = shape
+    rng = np.random.default_rng(1450 + h + tt + w)
+    abig = (rng.integers(-64, 64, size=(h + 6, tt + 10)) / 64).astype(np.float64)
+    bbig = (rng.integers(-64, 64, size=(tt + 4, w + 8)) / 64).astype(np.float64)
+    for views in (False, True):
+        res = []
+        for e in engines:
+            pa, pb = P.PDL.from_numpy(abig, T.D, e), P.PDL.from_numpy(bbig, T.D, e)
+            if views:   # even element offsets keep the 16-byte alignment TMA needs; odd ones must take the cp.async kernel
+                pa, pb = pa.slice(f"2:{tt + 1},4:{h + 3}"), pb.slice(f"6:{w + 5},2:{tt + 1}")
+            else:
+                pa, pb = pa.slice(f"0:{tt - 1},0:{h - 1}").copy(), pb.slice(f"0:{w - 1},0:{tt - 1}").copy()
+            res.append(P.matmult(pa, pb))
+            if e is cuda and h * w >= 128 * 128:
+                assert cuda.last_kernel() == "matmult_dmma_tma", cuda.last_kernel()
+        assert_same(f"matmult-tma-{shape}-views{views}", res[0], res[1])
+    res = []
+    for e in engines:   # odd offset: not 16-byte aligned -> the cp.async kernel, same answer
+        pa, pb = P.PDL.from_numpy(abig, T.D, e), P.PDL.from_numpy(bbig, T.D, e)
+        res.append(P.matmult(pa.slice(f"1:{tt},1:{h}"), pb.slice(f"3:{w + 2},1:{tt}")))
+    assert_same(f"matmult-unaligned-{shape}", res[0], res[1])
+
+
+@pytest.mark.parametrize("t", [T.SB, T.B, T.S, T.US], ids=lambda t: T.NAMES[t])
+def test_small_int_ind_two_phase(engines, t):
+    """minimum_ind / maximum_ind of 8/16-bit rows: packed value reduction + first-index search.  Rows with a unique
+    extreme at the very end / start / middle, rows that are one long tie, unaligned and strided rows, BAD rows."""
+    rng = np.random.default_rng(1460 + t)
+    dt = T.NP_DTYPE[t]
+    info = np.iinfo(dt)
+    for n, rows in ((40_003, 9), (70, 300), (33, 50), (5, 1000)):
+        a = rng.integers(max(info.min, -50), min(info.max, 50), size=(rows, n), endpoint=True).astype(dt)
+        a[0, :] = 7                                        # one long tie: index 0 wins
+        a[1, :] = 3; a[1, n - 1] = 99; a[1, 0] = -99 if info.min < 0 else 0   # unique max at the end, unique min at the start
+        a[2, :] = 5; a[2, n // 2] = 100                    # unique max in the middle
+        bad = np.array(T.DEFAULT_BAD[t]).astype(dt)
+        b = a.copy()
+        b[rng.random(b.shape) < 0.05] = bad
+        b[3, :] = bad                                      # all BAD -> BAD index
+        b[4, : n - 1] = bad                                # only the last element is good
+        for arr, flag in ((a, False), (b, True)):
+            for op in ("minimum_ind", "maximum_ind"):
+                (ga, oa) = both(engines, arr, t, flag)
+                assert_same(f"{op}-{T.NAMES[t]}-{n}x{rows}-{flag}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa))
+                if n > 40:
+                    assert_same(f"{op}-{T.NAMES[t]}-unaligned", getattr(ufunc, op)(ga.slice("3:-2,:")), getattr(ufunc, op)(oa.slice("3:-2,:")))
+                    assert_same(f"{op}-{T.NAMES[t]}-strided", getattr(ufunc, op)(ga.slice("1:-1:3,:")), getattr(ufunc, op)(oa.slice("1:-1:3,:")))
+                    assert_same(f"{op}-{T.NAMES[t]}-column", getattr(ufunc, op)(ga.xchg(0, 1)), getattr(ufunc, op)(oa.xchg(0, 1)))
+
+
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_divide_sqrt_fast_path_and_specials(engines, t):
+    """divide / sqrt evaluate a 16-byte unit straight-line and fall back per unit: ordinary values, and every kind of
+    special operand (zeros of both signs, infinities, NaNs, denormals, huge and tiny magnitudes) mixed into the SAME
+    units, must all be bit-identical to the reference's IEEE results."""
+    rng = np.random.default_rng(1470 + t)
+    dt = T.NP_DTYPE[t]
+    n = 400_003
+    a = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, size=n)).astype(dt)
+    b = (rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, size=n)).astype(dt)
+    tiny, huge = np.finfo(dt).tiny, np.finfo(dt).max
+    specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, tiny, -tiny, tiny / 4, huge, -huge, 1.0, 3.0,
+                         float(2.0 ** 41), float(2.0 ** -41), float(2.0 ** 100), float(2.0 ** -100)], dtype=dt)
+    idx = rng.choice(n, size=6000, replace=False)
+    a[idx[:3000]] = rng.choice(specials, size=3000)
+    b[idx[1500:4500]] = rng.choice(specials, size=3000)
+    with np.errstate(all="ignore"):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        assert_same(f"divide-specials-{T.NAMES[t]}", P.run_biop("divide", ga, gb), P.run_biop("divide", oa, ob))
+        assert_same(f"sqrt-specials-{T.NAMES[t]}", P.run_ufunc("sqrt", ga), P.run_ufunc("sqrt", oa))
+        bad = np.array(T.DEFAULT_BAD[t]).astype(dt)
+        a2, b2 = a.copy(), b.copy()
+        a2[rng.random(n) < 0.01] = bad
+        b2[rng.random(n) < 0.01] = bad
+        (ga, oa), (gb, ob) = both(engines, a2, t, True), both(engines, b2, t, True)
+        assert_same(f"divide-specials-bad-{T.NAMES[t]}", P.run_biop("divide", ga, gb), P.run_biop("divide", oa, ob))
+        assert_same(f"sqrt-specials-bad-{T.NAMES[t]}", P.run_ufunc("sqrt", ga), P.run_ufunc("sqrt", oa))
+
+
 @pytest.mark.parametrize("t", [T.B, T.S, T.L, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
 def test_scans(engines, t):
     rng = np.random.default_rng(1500 + t)

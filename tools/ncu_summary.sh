@@ -5,9 +5,9 @@
 set -u
 OUT="$1"; shift
 mkdir -p "$OUT"
-K="regex:reduce_rows_kernel|ew_tile_kernel|ew_kernel|mm_dmma|mm_exact_kernel|inner_warp_kernel|minmaximum_warp_kernel|scan_chunk_kernel|axisvals_kernel"
+K="regex:reduce_rows_kernel|ew_tile_kernel|ew_kernel|mm_dmma|mm_exact_kernel|inner_warp_kernel|minmaximum_warp_kernel|scan_chunk_kernel|axisvals_kernel|nind_kernel"
 for op in "$@"; do
-  REP=/tmp/prof_$op
+  REP=/tmp/prof_$(echo $op | tr ':' '_')
   ncu --set full --clock-control none --import-source on -k "$K" -s 1 -c 1 -f -o $REP python tools/prof_one.py $op 3 > /dev/null 2>&1
   ncu -i $REP.ncu-rep --page raw --csv 2>/dev/null | python3 -c '
 import csv, sys
@@ -22,7 +22,7 @@ if len(rows) >= 3:
     for h, u, v in zip(hdr, units, vals):
         if any(h.startswith(k) for k in keep):
             print(f"{h},{u},{v}")
-' > "$OUT/$op.raw.csv"
+' > "$OUT/$(echo $op | tr ':' '_').raw.csv"
   # hottest source lines by sampled stalls
   ncu -i $REP.ncu-rep --page source --csv 2>/dev/null | python3 -c '
 import csv, sys
@@ -40,7 +40,7 @@ if rows:
         print(",".join(hdr[:8]))
         for r in body[:40]:
             print(",".join(x.replace(",", ";")[:160] for x in r[:8]))
-' > "$OUT/$op.source_top.csv"
+' > "$OUT/$(echo $op | tr ':' '_').source_top.csv"
   rm -f $REP.ncu-rep
 done
 ls -la "$OUT"

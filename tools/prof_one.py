@@ -61,6 +61,25 @@ elif op in ("setbadif", "inner", "minmaximum", "cumusumover", "sequence"):
         f = P.prepare_op("cumusumover", [wrap(x, T.F, [16384, n // 16384])], [wrap(torch.empty_like(x), T.F, [16384, n // 16384])])
     else:
         f = P.prepare_op("axisvalues", [of], [of])
+elif op.startswith(("ew:", "rd:")):
+    # generic: ew:<op>:<type>:<good|bad> / rd:<op>:<type>:<good|bad> on 1 GiB operands (as tools/sweep.py)
+    kind, name, tname, mode = op.split(":")
+    t = T.NAMES.index(tname)
+    tt = {T.SB: torch.int8, T.B: torch.uint8, T.S: torch.int16, T.L: torch.int32, T.LL: torch.int64, T.F: torch.float32, T.D: torch.float64}[t]
+    n = (1 << 30) // T.SIZE[t]
+    a = torch.randint(0 if tt == torch.uint8 else -8, 9, (n,), device=dev, dtype=torch.int32).to(tt)
+    b = torch.randint(1, 9, (n,), device=dev, dtype=torch.int32).to(tt)
+    c = torch.empty_like(a)
+    bad = mode == "bad"
+    if kind == "ew":
+        pa, pb, pc = wrap(a, t, [n]), wrap(b, t, [n]), wrap(c, t, [n])
+        pa.badflag = pb.badflag = bad
+        f = P.prepare_op(name, [pa, pb] if len(P.SPECS[name].pars) == 3 else [pa], [pc])
+    else:
+        p2 = wrap(a, t, [16384, n // 16384])
+        p2.badflag = bad
+        ot = P.trans.par_type(P.SPECS[name].pars[1], t)
+        f = P.prepare_op(name, [p2], [P.PDL.empty(ot, [n // 16384], eng)])
 else:
     raise SystemExit(f"unknown op {op}")
 for _ in range(reps):
