@@ -217,6 +217,9 @@ PDLB200_API int    pdlb200_sm_count(void);
 PDLB200_API int    pdlb200_sync(void *stream, char *err, size_t errlen);
 /* Pinned host memory for the e2e path (host<->device copies at PCIe rate). */
 PDLB200_API void  *pdlb200_host_alloc(size_t nbytes);
+/* Same, write-combined: for staging buffers the host only fills sequentially and the GPU reads (H2D), the
+ * pages are not snooped, which helps when several GPUs pull from host memory at once. */
+PDLB200_API void  *pdlb200_host_alloc_wc(size_t nbytes);
 PDLB200_API void   pdlb200_host_free(void *p);
 PDLB200_API int    pdlb200_memcpy_h2d(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);
 PDLB200_API int    pdlb200_memcpy_d2h(void *dst, const void *src, size_t nbytes, void *stream, char *err, size_t errlen);

@@ -83,6 +83,7 @@ SYMBOLS = [
     "pdlb200_mbuf_new", "pdlb200_mbuf_adopt", "pdlb200_mbuf_retain", "pdlb200_mbuf_free", "pdlb200_mbuf_is",
     "pdlb200_mbuf_dev", "pdlb200_mbuf_host", "pdlb200_mbuf_state", "pdlb200_mbuf_stats", "pdlb200_mbuf_trim",
     "pdlb200_devop_register", "pdlb200_devop_is", "pdlb200_dev_alloc", "pdlb200_dev_free", "pdlb200_dev_trim",
+    "pdlb200_host_alloc_wc",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpdlb200.so"
@@ -133,6 +134,8 @@ def load():
     lib.pdlb200_sync.restype = C.c_int
     lib.pdlb200_host_alloc.argtypes = [C.c_size_t]
     lib.pdlb200_host_alloc.restype = C.c_void_p
+    lib.pdlb200_host_alloc_wc.argtypes = [C.c_size_t]
+    lib.pdlb200_host_alloc_wc.restype = C.c_void_p
     lib.pdlb200_host_free.argtypes = [C.c_void_p]
     lib.pdlb200_host_free.restype = None
     for name in ("pdlb200_memcpy_h2d", "pdlb200_memcpy_d2h"):

@@ -39,21 +39,23 @@ int sm_count() {
   return g_sm_count;
 }
 
-// scratch for two-stage reductions: one grow-only buffer per device, used in stream order.
-static void *g_scratch[16] = {nullptr};
-static size_t g_scratch_sz[16] = {0};
+// scratch for two-stage reductions / scans / flag words: one grow-only buffer per (device, stream), used in that
+// stream's order — two streams running scratch-using ops at the same time never share a buffer.
+struct ScratchBuf { void *p; size_t sz; };
+static std::unordered_map<uint64_t, ScratchBuf> g_scratch;
 void *scratch(size_t nbytes, cudaStream_t s) {
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 16) return nullptr;
+  const uint64_t key = ((uint64_t)(uintptr_t)s << 4) ^ (uint64_t)(dev & 15);
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_scratch_sz[dev] < nbytes) {
-    if (g_scratch[dev]) { cudaStreamSynchronize(s); cudaDeviceSynchronize(); cudaFree(g_scratch[dev]); }
-    size_t want = nbytes < (1u << 20) ? (1u << 20) : nbytes;
-    if (cudaMalloc(&g_scratch[dev], want) != cudaSuccess) { g_scratch[dev] = nullptr; g_scratch_sz[dev] = 0; return nullptr; }
-    g_scratch_sz[dev] = want;
+  ScratchBuf &b = g_scratch[key];
+  if (b.sz < nbytes) {
+    if (b.p) { cudaStreamSynchronize(s); cudaFree(b.p); }
+    const size_t want = nbytes < (1u << 20) ? (1u << 20) : nbytes;
+    if (cudaMalloc(&b.p, want) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; b.sz = 0; return nullptr; }
+    b.sz = want;
   }
-  return g_scratch[dev];
+  return b.p;
 }
 
 static std::unordered_multimap<size_t, void *> g_managed_free;   // exact-size free list
@@ -425,6 +427,12 @@ void *pdlb200_host_alloc(size_t nbytes) {
   if (probe_devices() <= 0) return nullptr;
   void *p = nullptr;
   if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void *pdlb200_host_alloc_wc(size_t nbytes) {
+  if (probe_devices() <= 0) return nullptr;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   return p;
 }
 void pdlb200_host_free(void *p) { if (p) cudaFreeHost(p); }

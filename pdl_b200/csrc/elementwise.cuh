@@ -260,14 +260,23 @@ __device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI>
     }
     rc.q = make_uint4(cw[0], cw[1], cw[2], cw[3]);
   } else if constexpr (op_packfloat<Op>::value && !tt<TI>::is_int && std::is_same<TI, TO>::value && std::is_same<TI, TB>::value) {
-    Op::template fpack<TI, VEC>(ra, rb, rc);
     if constexpr (BAD) {
+      // BAD lanes (type-min / huge badvalues) would push the whole unit onto the op's rare path: give them a
+      // harmless operand pair (1 op 1) first, then put the output badvalue in their place
+      Pack<TI> ma; Pack<TB> mb;
+      bool bad[VEC];
 #pragma unroll
       for (int k = 0; k < VEC; k++) {
-        bool bad = p.badchk[0] && is_bad(ra.e[k], abad, p.badnan[0] != 0);
-        if (NIN > 1) bad = bad || (p.badchk[1] && is_bad(rb.e[k], bbad, p.badnan[1] != 0));
-        rc.e[k] = bad ? cbad : rc.e[k];
+        bad[k] = p.badchk[0] && is_bad(ra.e[k], abad, p.badnan[0] != 0);
+        if (NIN > 1) bad[k] = bad[k] || (p.badchk[1] && is_bad(rb.e[k], bbad, p.badnan[1] != 0));
+        ma.e[k] = bad[k] ? TI(1) : ra.e[k];
+        mb.e[k] = (NIN > 1) ? (bad[k] ? TB(1) : rb.e[k]) : TB(1);
       }
+      Op::template fpack<TI, VEC>(ma, mb, rc);
+#pragma unroll
+      for (int k = 0; k < VEC; k++) rc.e[k] = bad[k] ? cbad : rc.e[k];
+    } else {
+      Op::template fpack<TI, VEC>(ra, rb, rc);
     }
   } else {
 #pragma unroll

@@ -148,9 +148,10 @@ def test_long_row_scan_chunked(cuda_engine):
 
 @pytest.mark.parametrize("case", ["float-2rows-bad", "double-prod", "int64-sum", "int32-3rows-tail"])
 def test_lookback_scan_variants(cuda_engine, case):
-    """The single-pass look-back scan (rows >= 64 tiles of 64 KB, unit-stride, 16-byte aligned): BAD elements,
-    several rows, products, 64-bit accumulators, rows ending inside a vector — against torch's cumsum/cumprod
-    on inputs whose partial results are exactly representable."""
+    """Long-row scans (the chunked three-pass scheme: chunk totals, exclusive scan of the totals, scan with carry-in;
+    the case names date from the look-back experiments recorded in DESIGN.md §4): BAD elements, several rows,
+    products, 64-bit accumulators, rows ending inside a vector — against torch's cumsum/cumprod on inputs whose
+    partial results are exactly representable."""
     g = torch.Generator(device="cuda").manual_seed(23)
     if case == "float-2rows-bad":
         n = 2**22 + 8                                   # rows stay 16-byte aligned

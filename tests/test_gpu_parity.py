@@ -269,7 +269,7 @@ def test_matmult_tma_tiles_edges_and_views(engines, shape):
             else:
                 pa, pb = pa.slice(f"0:{tt - 1},0:{h - 1}").copy(), pb.slice(f"0:{w - 1},0:{tt - 1}").copy()
             res.append(P.matmult(pa, pb))
-            if e is cuda and h * w >= 128 * 128:
+            if e is cuda and h * w >= 128 * 128 and tt % 2 == 0 and w % 2 == 0:   # row pitches are multiples of 16 bytes
                 assert cuda.last_kernel() == "matmult_dmma_tma", cuda.last_kernel()
         assert_same(f"matmult-tma-{shape}-views{views}", res[0], res[1])
     res = []
