@@ -121,6 +121,25 @@ def generate_cfg5(torch, g0: int, count: int, device, plant_at: int = -1, plant_
     return out, total
 
 
+def _bind_near_gpu(torch, local: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that host staging memory is
+    allocated there.  Returns the node number, or None when the topology cannot be read."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / dev
+        node = int((base / "numa_node").read_text().strip())
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 def _clock_sampler(stop, samples):
     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -367,8 +386,19 @@ def main_ours(args):
     # ---- e2e: pinned host ndarray -> H2D -> 3 reductions -> D2H, per step ----
     e2e_steps = max(1, min(args.steps, 5))
     nbytes_in = N_DIM * ROWS * 4
-    host_in = torch.empty((ROWS, N_DIM), dtype=torch.float32, pin_memory=True)
-    host_in.copy_(dev_in)
+    # staging memory near the GPU: run this rank on the CPUs of the GPU's NUMA node while the pinned buffer is
+    # created (first touch places the pages there), and make it write-combined (the host only fills it, the GPU's
+    # DMA reads it) — with 8 ranks pulling 4 GiB each, cross-socket traffic and snooping were what capped N = 8
+    old_affinity = os.sched_getaffinity(0)
+    numa = _bind_near_gpu(torch, local)
+    host_ptr = eng.lib.pdlb200_host_alloc_wc(nbytes_in)
+    staging = "write-combined pinned"
+    if not host_ptr:
+        host_ptr = eng.lib.pdlb200_host_alloc(nbytes_in)
+        staging = "pinned"
+    eng.download_ptr(a.store, host_ptr, nbytes_in)
+    eng.sync()
+    os.sched_setaffinity(0, old_affinity)      # only the allocation is placed; the CPU legs below use every core again
     host_out = torch.empty((3, ROWS), dtype=torch.float32, pin_memory=True)
     stage = torch.empty((ROWS, N_DIM), dtype=torch.float32, device=device)
     sa = P.PDL(eng, eng.wrap(stage.data_ptr(), nbytes_in, stage), T.F, [N_DIM, ROWS]).set_badflag(True)
@@ -386,7 +416,7 @@ def main_ours(args):
         for s in range(SLABS):
             off = s * rows_slab * N_DIM * 4
             eng.stream = copy_s.cuda_stream
-            eng.upload_ptr(sa.store, host_in.data_ptr() + off, rows_slab * N_DIM * 4, off)
+            eng.upload_ptr(sa.store, host_ptr + off, rows_slab * N_DIM * 4, off)
             evs[s].record(copy_s)
             comp_s.wait_event(evs[s])
             eng.stream = comp_s.cuda_stream
@@ -423,6 +453,11 @@ def main_ours(args):
             gt.copy_(lt)
 
     comm = parallel.Comm() if dist is not None else _Solo()
+    # records travel over peer memory (one kernel: NVLink stores + epoch flags) when the GPUs can map each other
+    exchange = "device copy (1 rank)"
+    if dist is not None:
+        exchange = "peer-memory kernel (NVLink P2P, CUDA IPC mailboxes)" if (not args.nccl_gather and comm.enable_peer_exchange(eng)) \
+            else "ncclAllGather"
 
     def cfg5_leg(per_gpu: int, label: str):
         total_n = per_gpu * world
@@ -467,7 +502,7 @@ def main_ours(args):
         return {"workload": label, "api": "pdl_b200.parallel.pcollapse(flat, comm, ('sum','max'))",
                 "ms_per_step": ms, "elements_per_sec": 2 * total_n / (ms / 1e3),
                 "gbs_per_gpu": 2 * per_gpu * 4 / ms / 1e6, "frac_per_gpu": 2 * per_gpu * 4 / ms / 1e6 / peak,
-                "launches_per_step": int(nl), "collectives_per_step": 1 if world > 1 else 0,
+                "launches_per_step": int(nl), "exchanges_per_step": 1 if world > 1 else 0, "exchange": exchange,
                 "sum": float(got_sum), "max": float(got_max), "max_ind": got_ind, "verified": bool(ok)}
 
     cfg5_extra = cfg5_leg(N_DIM * ROWS, f"cfg5: sum+max of float[2^30 x {world}] sharded over {world} GPU(s), weak")
@@ -524,7 +559,7 @@ def main_ours(args):
                    "l2": "inputs (4 GiB per GPU) larger than L2", "timer": "cuda events, max over ranks"},
         "roofline": roofline, "per_op": per_op,
         "e2e": {"value": e2e_value, "unit": "elements/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": 3 * ROWS * 4,
-                "steps": e2e_steps, "slabs": SLABS, "matches_resident_result": e2e_ok},
+                "steps": e2e_steps, "slabs": SLABS, "matches_resident_result": e2e_ok, "staging": staging, "numa_node": numa},
         "gpu_launches": int(launches),
         "clocks": dict(_clocks_summary(samples), window="timed steps + per-op loops + 1.5 s sustained loop of the same step"),
         "sustained": {"ms_per_step": sustained_ms, "steps": sustained_steps,
@@ -544,5 +579,6 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg1/cfg3/cfg4/perl legs")
+    ap.add_argument("--nccl-gather", action="store_true", help="cfg5: exchange the records with ncclAllGather instead of the peer-memory kernel")
     a = ap.parse_args()
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

