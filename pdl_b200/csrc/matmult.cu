@@ -30,6 +30,19 @@ template <> struct mm_acc<uint32_t> { using type = uint32_t; };
 template <> struct mm_acc<int64_t>  { using type = uint64_t; };
 template <> struct mm_acc<uint64_t> { using type = uint64_t; };
 
+// One output element in the reference's own order with the x86 NaN rules at every step: the slow, exact twin of the
+// hot loop, run only for outputs whose fast sum came out NaN.
+template <class T>
+__device__ __noinline__ T mm_nan_elem(const T *a, const T *b, int64_t tn, int64_t iat, int64_t ibt) {
+  T cc = T(0);
+  for (int64_t t = 0; t < tn; t++) {
+    const T x = a[t * iat], y = b[t * ibt];
+    const T m = x86_nan2(x, y, x * y);
+    cc = x86_nan2(cc, m, cc + m);
+  }
+  return cc;
+}
+
 template <class T, bool BAD>
 __global__ void __launch_bounds__(256)
 mm_exact_kernel(const __grid_constant__ MmPlan p) {
@@ -114,9 +127,13 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
               if (frozen[i][j]) continue;
             }
             if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
-            else {  // two roundings (and x86 NaN rules), as on the reference's x86-64 build
+            else if constexpr (BAD) {  // two roundings (and x86 NaN rules), as on the reference's x86-64 build
               const T m = x86_nan2(av[i], bv[j], av[i] * bv[j]);
               acc[i][j] = x86_nan2(acc[i][j], m, acc[i][j] + m);
+            } else {
+              // good mode: plain multiply then add (two roundings, -fmad=false).  A NaN is sticky in a sum, so its
+              // x86 sign/payload rules are applied afterwards, only to the outputs that ended up NaN (mm_nan_elem)
+              acc[i][j] = acc[i][j] + av[i] * bv[j];
             }
           }
       }
@@ -131,6 +148,7 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
       if (h < p.H && w < p.W) {
         T out = (T)acc[i][j];
         if (BAD && frozen[i][j] == 2) out = cbad;
+        if constexpr (!BAD && !tt<T>::is_int) { if (out != out) out = mm_nan_elem<T>(Ap + h * p.iah, Bp + w * p.ibw, p.T, p.iat, p.ibt); }
         Cp[w * p.icw + h * p.ich] = out;
       }
     }
