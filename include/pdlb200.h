@@ -38,13 +38,19 @@ extern "C" {
 
 /* Element types: numeric values are PDL's own pdl_datatypes enum
  * (lib/PDL/Types.pm:27-255, order is significant for promotion).
- * LD/CF/CD/CLD (11..14) are not implemented on the device: LD/CLD are x87
- * 80-bit and have no GPU representation. */
+ * LD/CLD (11, 14) are x87 80-bit and have no GPU representation. */
 enum {
   PDLB200_SB = 0, PDLB200_B = 1, PDLB200_S = 2, PDLB200_US = 3, PDLB200_L = 4,
   PDLB200_UL = 5, PDLB200_IND = 6, PDLB200_ULL = 7, PDLB200_LL = 8,
   PDLB200_F = 9, PDLB200_D = 10,
-  PDLB200_NTYPES = 11
+  PDLB200_NTYPES = 11,
+  /* Complex float / double (C99 `float complex` / `double complex`, interleaved re, im): on the device path for
+   * plus minus mult divide only (lib/PDL/Ops.pd:104-153,288-291).  mult is the compiler's inline
+   * (ac-bd, ad+bc) with libgcc's __mulsc3/__muldc3 recovery of infinities, divide is libgcc's __divsc3 (in double)
+   * / __divdc3 (scaled Smith), restated operation for operation.  `badval`: CF carries both parts (re in the low
+   * 4 bytes); CD carries the bits of the REAL part and requires the imaginary part of the badvalue to be equal
+   * (true of the default -DBL_MAX - DBL_MAX*i). */
+  PDLB200_LD = 11, PDLB200_CF = 12, PDLB200_CD = 13, PDLB200_CLD = 14
 };
 
 /* Operations.  Each names the reference pp_def whose readdata it replaces. */

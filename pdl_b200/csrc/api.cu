@@ -114,7 +114,8 @@ static int validate(const pdlb200_trans *t, const Err &E) {
   if (t->op < 0 || t->op >= PDLB200_OP__END || !pdlb200_op_name(t->op)[0])
     return E.fail(PDLB200_EINVAL, "pdlb200: unknown op %d", t->op);
   if (t->datatype < 0) return E.fail(PDLB200_EINVAL, "%s: invalid datatype %d", pdlb200_op_name(t->op), t->datatype);
-  if (t->datatype >= PDLB200_NTYPES)
+  const bool cplx = (t->datatype == PDLB200_CF || t->datatype == PDLB200_CD) && t->op >= PDLB200_OP_PLUS && t->op <= PDLB200_OP_DIVIDE;
+  if (t->datatype >= PDLB200_NTYPES && !cplx)
     return E.fail(PDLB200_EUNSUPPORTED, "%s: type %d (long double / complex) has no device representation",
                   pdlb200_op_name(t->op), t->datatype);
   if (t->ndims < 0 || t->ndims > PDLB200_MAXDIMS)
@@ -136,6 +137,7 @@ int ew_unary(const pdlb200_trans *, const Err &);
 
 int launch_elementwise(const pdlb200_trans *t, const Err &E) {
   const int op = t->op;
+  if (t->datatype == PDLB200_CF || t->datatype == PDLB200_CD) return launch_complex(t, E);
   if (op <= PDLB200_OP_DIVIDE || op == PDLB200_OP_OUTER) return ew_arith(t, E);
   if (op <= PDLB200_OP_NE) return ew_cmp(t, E);
   if (op <= PDLB200_OP_XOR || op == PDLB200_OP_BITNOT) return ew_bits(t, E);
@@ -165,8 +167,8 @@ const char *pdlb200_op_name(int op) {
   return op_names[op];
 }
 size_t pdlb200_type_size(int type) {
-  static const size_t sz[PDLB200_NTYPES] = {1, 1, 2, 2, 4, 4, 8, 8, 8, 4, 8};
-  return (type >= 0 && type < PDLB200_NTYPES) ? sz[type] : 0;
+  static const size_t sz[15] = {1, 1, 2, 2, 4, 4, 8, 8, 8, 4, 8, 0, 8, 16, 0};
+  return (type >= 0 && type < 15) ? sz[type] : 0;
 }
 
 int pdlb200_set_device(int dev, char *err, size_t errlen) {

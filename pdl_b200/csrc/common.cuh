@@ -116,6 +116,7 @@ int launch_scan(const pdlb200_trans *t, const Err &E);
 int launch_partial(const pdlb200_trans *t, const Err &E);
 int launch_collapse(const pdlb200_trans *t, const Err &E);
 int launch_nind(const pdlb200_trans *t, const Err &E);
+int launch_complex(const pdlb200_trans *t, const Err &E);
 int launch_matmult(const pdlb200_trans *t, const Err &E);
 
 // per-device scratch for two-stage reductions (api.cu); grows, never shrinks

@@ -38,6 +38,10 @@ elif op == "mult_cfg3":
     pr = torch.empty(N * N, dtype=torch.float64, device=dev)
     f = P.prepare_op("mult", [wrap(b1, T.D, [2 * N]).slice("0:-1:2").dummy(1, 1),
                               wrap(b2, T.D, [2 * N]).slice("0:-1:2").dummy(0, 1)], [wrap(pr, T.D, [N, N])])
+elif op == "matmult_exact_float":
+    n = 4096
+    A, B, Cc = (torch.randint(-8, 8, (n, n), device=dev).float() for _ in range(3))
+    f = P.prepare_op("matmult", [wrap(A, T.F, [n, n]), wrap(B, T.F, [n, n])], [wrap(Cc, T.F, [n, n])])
 elif op == "matmult":
     n = 4096
     A, B, Cc = (torch.rand((n, n), dtype=torch.float64, device=dev) for _ in range(3))
