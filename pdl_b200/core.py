@@ -160,6 +160,9 @@ class PDL:
 
     def badvalue_isnan(self) -> bool:
         v = self.badvalue
+        if self.datatype in (T.CF, T.CD):
+            v = complex(v)
+            return math.isnan(v.real) or math.isnan(v.imag)
         return self.datatype in (T.F, T.D) and isinstance(v, float) and math.isnan(v)
 
     def set_badflag(self, flag: bool = True) -> "PDL":
@@ -328,10 +331,21 @@ class PDL:
     def flat(self) -> "PDL":
         return self if self.ndims == 1 else self.clump(-1)
 
+    def _as_words(self) -> "PDL":
+        """A complex ndarray seen as 64-bit words (cfloat: one per element; cdouble: a leading dim of 2), for ops that
+        only move bits."""
+        if self.datatype == T.CF:
+            return PDL(self.engine, self.store, T.LL, self.dims, self.dimincs, self.offs)
+        return PDL(self.engine, self.store, T.LL, [2] + self.dims, [1] + [2 * i for i in self.dimincs], 2 * self.offs)
+
     def copy(self) -> "PDL":
         out = PDL.empty(self.datatype, self.dims, self.engine)
         out._badvalue = self._badvalue
         from .trans import run_op
+        if self.datatype in (T.CF, T.CD):        # complex: a bit copy through the 64-bit assgn kernel
+            run_op("assgn", [self._as_words()], [out._as_words()])
+            out.badflag = self.badflag
+            return out
         run_op("assgn", [self], [out])
         return out
 

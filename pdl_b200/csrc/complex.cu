@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(EW_THREADS) cx_kernel(const __grid_constant__ 
     Cx<R> c;
     bool bad = false;
     if constexpr (BAD) {
-      bad = (p.badchk[0] && a.re == abad.re && a.im == abad.im) || (p.badchk[1] && b.re == bbad.re && b.im == bbad.im);
+      // PDL_ISBAD2 on a complex type: `==` on both parts, or (NaN badvalue) isnan of either part (Types.pm:209-232)
+      const bool ia = p.badnan[0] ? (a.re != a.re || a.im != a.im) : (a.re == abad.re && a.im == abad.im);
+      const bool ib = p.badnan[1] ? (b.re != b.re || b.im != b.im) : (b.re == bbad.re && b.im == bbad.im);
+      bad = (p.badchk[0] && ia) || (p.badchk[1] && ib);
     }
     if (bad) c = cbad; else c = cx_apply<R, OP>(a, b);
     reinterpret_cast<Cx<R> *>(p.ptr[2])[oc] = c;

@@ -201,6 +201,13 @@ def par_type(par: Par, transtype: int) -> int:
 def convert_type(p: PDL, datatype: int) -> PDL:
     """converttype on the device (lib/PDL/Core/pdlconv.c:45-126): BAD maps to the TARGET
     type's default badvalue; the result has no per-ndarray badvalue."""
+    if datatype in (T.CF, T.CD) and T.is_device_type(p.datatype) or (p.datatype in (T.CF, T.CD) and datatype in (T.CF, T.CD)):
+        # real -> complex (imaginary part 0) and complex -> complex: host-side glue of the mirror (the Perl binding
+        # leaves conversions that involve complex types to the reference's own converttypei)
+        src = p.to_numpy()
+        out = PDL.from_numpy(src.astype(T.NP_DTYPE[datatype]), datatype, p.engine)
+        out.badflag = p.badflag
+        return out
     if not T.is_device_type(datatype) or not T.is_device_type(p.datatype):
         raise PDLError(f"type {T.NAMES[datatype]} has no device representation")
     out = PDL.empty(datatype, p.dims, p.engine)
@@ -446,9 +453,9 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
 
     all_pdls = ins + outs
     transtype = transtype_select(spec, all_pdls)
-    if not T.is_device_type(transtype):
+    if not T.is_device_type_for(transtype, name):
         raise PDLError(f"PDL::{name}: type {T.NAMES[transtype]} has no device representation "
-                       "(long double / complex are outside the device type matrix)")
+                       "(long double, and complex outside + - * /, are outside the device type matrix)")
     # inputs to the type the loop is instantiated for (converttypei -> device convert kernel)
     if _prepare and any(x.datatype != par_type(par, transtype) for x, par in zip(ins, in_pars)):
         raise PDLError(f"PDL::{name}: prepare_op needs inputs already in the operation's type")

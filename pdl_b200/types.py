@@ -23,6 +23,7 @@ NP_DTYPE = {
     SB: np.dtype(np.int8), B: np.dtype(np.uint8), S: np.dtype(np.int16), US: np.dtype(np.uint16),
     L: np.dtype(np.int32), UL: np.dtype(np.uint32), IND: np.dtype(np.int64), ULL: np.dtype(np.uint64),
     LL: np.dtype(np.int64), F: np.dtype(np.float32), D: np.dtype(np.float64),
+    CF: np.dtype(np.complex64), CD: np.dtype(np.complex128),     # on the device path for + - * / only
 }
 SIZE = {t: d.itemsize for t, d in NP_DTYPE.items()}
 
@@ -39,6 +40,7 @@ _DBL_MAX = float(np.finfo(np.float64).max)
 DEFAULT_BAD = {
     SB: -128, B: 255, S: -32768, US: 65535, L: -2**31, UL: 2**32 - 1,
     IND: -2**63, ULL: 2**64 - 1, LL: -2**63, F: -_FLT_MAX, D: -_DBL_MAX,
+    CF: complex(-_FLT_MAX, -_FLT_MAX), CD: complex(-_DBL_MAX, -_DBL_MAX),      # Types.pm:209-232 defbval
 }
 
 
@@ -50,9 +52,17 @@ def is_device_type(t: int) -> bool:
     return 0 <= t < NTYPES_DEVICE
 
 
+COMPLEX_DEVICE_OPS = ("plus", "minus", "mult", "divide")
+
+
+def is_device_type_for(t: int, opname: str) -> bool:
+    """The device type matrix: the 11 real types for every op, complex float/double for + - * / only."""
+    return is_device_type(t) or (t in (CF, CD) and opname in COMPLEX_DEVICE_OPS)
+
+
 def from_numpy_dtype(dt) -> int:
     dt = np.dtype(dt)
-    for t in (SB, B, S, US, L, UL, LL, ULL, F, D):  # int64 maps to longlong (PDL's `longlong`); indx on request
+    for t in (SB, B, S, US, L, UL, LL, ULL, F, D, CF, CD):  # int64 maps to longlong (PDL's `longlong`); indx on request
         if NP_DTYPE[t] == dt:
             return t
     if dt == np.dtype(bool):
@@ -63,6 +73,13 @@ def from_numpy_dtype(dt) -> int:
 def value_bits(t: int, value) -> int:
     """Bit pattern (low-order bytes, little endian) of `value` stored as type t."""
     dt = NP_DTYPE[t]
+    if t in (CF, CD):
+        # CF: both parts (re in the low 4 bytes); CD: the REAL part's bits, the imaginary part must be equal
+        v = complex(value)
+        if t == CD and v.imag != v.real and not (v.imag != v.imag and v.real != v.real):
+            raise ValueError("a cdouble badvalue needs equal real and imaginary parts on the device path")
+        raw = np.array([v]).astype(dt).tobytes()[:8]
+        return int.from_bytes(raw, "little")
     with np.errstate(over="ignore"):
         arr = np.array([value]).astype(dt) if not isinstance(value, float) or t in (F, D) else np.array([int(value)]).astype(dt)
     raw = arr.tobytes()

@@ -29,6 +29,7 @@
 #ifndef PDLB200_PP_H
 #define PDLB200_PP_H
 
+#include <complex.h>
 #include "pdlb200.h"
 
 #define PDLB200_STAGE_DEFAULT 65536          /* parameters up to this many bytes are staged, not adopted */
@@ -61,8 +62,25 @@ static void pdlb200_pp_free_store(pdl *it, Size_t param) {
   if (it->data && pdlb200_mbuf_is(it->data)) { pdlb200_mbuf_free(it->data); it->data = NULL; }
 }
 
+/* complex float / complex double are on the device path for plus minus mult divide (include/pdlb200.h) */
+static int pdlb200_pp_type_ok(int datatype, int opid) {
+  if (datatype <= PDL_D) return 1;
+  return (datatype == PDL_CF || datatype == PDL_CD) && opid >= PDLB200_OP_PLUS && opid <= PDLB200_OP_DIVIDE;
+}
+
 static uint64_t pdlb200_pp_badval_bits(Core *PDLc, pdl *p) {
   uint64_t bits = 0;
+  if (p->datatype == PDL_CF) {            /* both parts, real part in the low 4 bytes */
+    complex float v = p->has_badvalue ? p->badvalue.value.G : PDLc->bvals.G;
+    memcpy(&bits, &v, 8);
+    return bits;
+  }
+  if (p->datatype == PDL_CD) {            /* the real part's bits (the ABI needs equal parts: checked by the caller) */
+    complex double v = p->has_badvalue ? p->badvalue.value.C : PDLc->bvals.C;
+    double re = creal(v);
+    memcpy(&bits, &re, 8);
+    return bits;
+  }
 #define X(sym, ctype, ppsym, ...) \
   case sym: { ctype v = p->has_badvalue ? p->badvalue.value.ppsym : PDLc->bvals.ppsym; memcpy(&bits, &v, sizeof v <= 8 ? sizeof v : 8); } break;
   switch (p->datatype) {
@@ -72,7 +90,15 @@ static uint64_t pdlb200_pp_badval_bits(Core *PDLc, pdl *p) {
 #undef X
   return bits;
 }
+static int pdlb200_pp_cd_badval_ok(Core *PDLc, pdl *p) {
+  complex double v;
+  if (p->datatype != PDL_CD) return 1;
+  v = p->has_badvalue ? p->badvalue.value.C : PDLc->bvals.C;
+  return creal(v) == cimag(v) || (creal(v) != creal(v) && cimag(v) != cimag(v));
+}
 static int pdlb200_pp_badval_isnan(Core *PDLc, pdl *p) {
+  if (p->datatype == PDL_CF) { complex float v = p->has_badvalue ? p->badvalue.value.G : PDLc->bvals.G; return crealf(v) != crealf(v) || cimagf(v) != cimagf(v); }
+  if (p->datatype == PDL_CD) { complex double v = p->has_badvalue ? p->badvalue.value.C : PDLc->bvals.C; return creal(v) != creal(v) || cimag(v) != cimag(v); }
   if (p->datatype == PDL_F) { float v = p->has_badvalue ? p->badvalue.value.F : PDLc->bvals.F; return v != v; }
   if (p->datatype == PDL_D) { double v = p->has_badvalue ? p->badvalue.value.D : PDLc->bvals.D; return v != v; }
   return 0;
@@ -198,11 +224,11 @@ static int pdlb200_pp_finish_staged(pdlb200_pp_staged_t *st, int nst, int need_s
 /* store buffers for the outputs this transformation creates, BEFORE core would allocate + zero-fill an SV */
 static void pdlb200_pp_give_outputs(Core *PDLc, pdl_trans *tr) {
   PDL_Indx i;
-  if (!pdlb200_pp_enabled || tr->__datatype > PDL_D || pdlb200_pp_init() != 0) return;
+  if (!pdlb200_pp_enabled || tr->__datatype > PDL_CD || tr->__datatype == PDL_LD || pdlb200_pp_init() != 0) return;
   for (i = tr->vtable->nparents; i < tr->vtable->npdls; i++) {
     pdl *o = tr->pdls[i];
     PDL_Indx nbytes;
-    if (!o || (o->state & PDL_ALLOCATED) || o->data || o->datatype > PDL_D || o->nvals <= 0) continue;
+    if (!o || (o->state & PDL_ALLOCATED) || o->data || o->datatype > PDL_CD || o->datatype == PDL_LD || o->nvals <= 0) continue;
     if (o->trans_parent != tr) continue;       /* only ndarrays this op creates */
     nbytes = o->nvals * (PDL_Indx)PDLc->howbig(o->datatype);
     if ((size_t)nbytes <= pdlb200_pp_stage_max || (size_t)nbytes <= sizeof(o->value)) continue;  /* small outputs keep core's inline / SV storage */
@@ -233,8 +259,9 @@ static pdl_error pdlb200_pp_readdata(Core *PDLc, pdl_trans *tr, int opid, pdlb20
   int32_t anybad = 0;
   PDL_Indx i, j, npdls = vt->npdls;
   char err[512];
-  if (tr->__datatype > PDL_D || npdls > PDLB200_MAXPDLS || tr->broadcast.ndims > PDLB200_MAXDIMS) on_device = 0;
-  for (j = 0; on_device && j < npdls; j++) if (tr->pdls[j]->datatype > PDL_D) on_device = 0;
+  if (!pdlb200_pp_type_ok(tr->__datatype, opid) || npdls > PDLB200_MAXPDLS || tr->broadcast.ndims > PDLB200_MAXDIMS) on_device = 0;
+  for (j = 0; on_device && j < npdls; j++)
+    if (!pdlb200_pp_type_ok(tr->pdls[j]->datatype, opid) || !pdlb200_pp_cd_badval_ok(PDLc, tr->pdls[j])) on_device = 0;
   if (!on_device) {
     if (fallback) {
       /* the reference's own host loop: its parameters must be current in host memory */

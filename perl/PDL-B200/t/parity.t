@@ -109,6 +109,17 @@ for my $t (@types) {
     both("isnan $t",             sub { $sp->isnan });
   }
 }
+# complex float / double: plus minus mult divide run on the device (gcc's inline multiply, libgcc's division restated)
+for my $t (cfloat, cdouble) {
+  my $rt = $t == cfloat ? float : double;
+  my $za = PDL::czip(mk($rt, 300, 7), mk($rt, 300, 7)); my $zb = PDL::czip(mk($rt, 300, 7), mk($rt, 300, 7) + 0.5);
+  both("complex plus $t",   sub { $za + $zb });
+  both("complex minus $t",  sub { $za - $zb });
+  both("complex mult $t",   sub { $za * $zb });
+  both("complex divide $t", sub { $za / $zb });
+  both("complex times real scalar $t", sub { $za * 2.5 });
+  both("complex broadcast $t", sub { $za / $zb->slice(':,(3)') });
+}
 # large: exercises the device store (outputs created in it, inputs adopted on first use)
 {
   my $y = sequence(2048, 2048); my $c = sequence(2048, 2048) * 0.5 + 1;

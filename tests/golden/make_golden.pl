@@ -538,3 +538,32 @@ for my $t (qw(float double)) {
 }
 add_case("minimum_n_ind-too-many", [[mk('double',[3],'small')]], {kind=>'n_ind', op=>'minimum_n_ind', m=>4});
 flush_cases('round2.json');
+
+# ---------------------------------------------------------------- complex float / double: plus minus mult divide (Ops.pd:104-153,288-291)
+$TOBJ{cfloat} = PDL::Type->new('cfloat'); $TOBJ{cdouble} = PDL::Type->new('cdouble');
+for my $t (qw(cfloat cdouble)) {
+  my $rt = $t eq 'cfloat' ? 'float' : 'double';
+  my $mkc = sub { my ($dims, $fl) = @_; PDL::czip(mk($rt, $dims, $fl), mk($rt, $dims, $fl)) };
+  my ($big, $tiny, $sub) = $t eq 'cfloat' ? (1e30, 1e-30, 1e-40) : (1e300, 1e-300, 1e-310);
+  # magnitudes that reach every scaling branch of libgcc's __divdc3 (near overflow, near underflow, denormals, tiny ratios)
+  my $ext = PDL::czip(pdl($TOBJ{$rt}, [$big, $tiny, $sub, 1, $big, $tiny, 3, -$big, $sub, 0, 1e10, $big]),
+                      pdl($TOBJ{$rt}, [$big, $tiny, 1, $sub, $tiny, $big, -4, 2, $sub, 0, $tiny, -$big]));
+  my $ext2 = PDL::czip(pdl($TOBJ{$rt}, [$big, $tiny, $tiny, $big, 1, 2, $sub, $big, 1, 1, $big, $tiny]),
+                       pdl($TOBJ{$rt}, [$tiny, $big, $sub, $big, $sub, -2, 1, $big, $big, 0, 1e-10, $tiny]));
+  my $spec = PDL::czip(mk($rt, [22], 'special'), mk($rt, [22], 'special'));
+  my $spec2 = PDL::czip(mk($rt, [22], 'special'), mk($rt, [22], 'small'));
+  for my $op (qw(plus minus mult divide)) {
+    add_case("$op-$t", [[$mkc->([7,3],'mixed')], [$mkc->([7,3],'mixed')]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-small", [[$mkc->([50],'small')], [$mkc->([50],'pos')]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-broadcast", [[$mkc->([5,4],'small')], [$mkc->([5],'pos')]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-strided", [[$mkc->([12,3],'small'), [['slice','-1:0:-2,:']]], [$mkc->([6],'pos')]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-swap-real-scalar", [[$mkc->([6],'small')], {scalar=>2.5}], {kind=>'biop', op=>$op, swap=>1});
+    add_case("$op-$t-extreme", [[$ext], [$ext2]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-extreme-swapped", [[$ext2], [$ext]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-special", [[$spec], [$spec2]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-special-swapped", [[$spec2], [$spec]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-bad", [[with_bad($mkc->([9,2],'small'), 1, 5, 11)], [with_bad($mkc->([9,2],'pos'), 0, 5)]], {kind=>'biop', op=>$op});
+    add_case("$op-$t-inplace", [[$mkc->([8],'small')], [$mkc->([8],'pos')]], {kind=>'biop', op=>$op, inplace=>1});
+  }
+}
+flush_cases('complex.json');

@@ -30,7 +30,7 @@ def build_input(spec, engine):
     bv = np.frombuffer(bytes.fromhex(spec["badvalue_hex"]), dtype=T.NP_DTYPE[t])[0]
     default = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
     if bv.tobytes() != default.tobytes():
-        p.set_badvalue(float(bv) if t in (T.F, T.D) else int(bv))
+        p.set_badvalue(complex(bv) if t in (T.CF, T.CD) else float(bv) if t in (T.F, T.D) else int(bv))
     for v in spec.get("views", []):
         p = getattr(p, v[0])(*v[1:])
     return p
@@ -137,7 +137,13 @@ def check_case(case, engine):
     # artefact of summation order and of x86-vs-GPU NaN generation, not of PDL semantics
     nan_free = (case["call"]["kind"] in ("reduce", "whole") and any(
         k in case["call"]["op"] for k in ("sum", "prod", "aver", "avg", "magn"))) or case["call"]["kind"] == "inner"
-    if dt.kind == "f" and (tol or nan_free):
+    if dt.kind == "c":
+        # complex results: NaN parts must be NaN on both sides (payload / sign of a NaN is an x86-vs-GPU artefact),
+        # every other part bit for bit
+        ft = np.float32 if dt == np.complex64 else np.float64
+        d = ulp_diff(got.view(ft), exp.view(ft))
+        assert d == 0, (case["name"], f"{d} ulp", got, exp)
+    elif dt.kind == "f" and (tol or nan_free):
         tol = tol or 0
         d = ulp_diff(got, exp)
         assert d <= tol, (case["name"], f"{d} ulp > {tol}", got, exp)

@@ -6,7 +6,7 @@ import pytest
 from replay import check_case, load_cases
 
 FILES = ["biop.json", "bifunc.json", "ufunc.json", "coerce.json", "broadcast.json", "bad.json",
-         "reduce.json", "matmult.json", "badops.json", "basic.json", "inner.json", "minmax.json", "outer.json", "edge.json", "round2.json"]
+         "reduce.json", "matmult.json", "badops.json", "basic.json", "inner.json", "minmax.json", "outer.json", "edge.json", "round2.json", "complex.json"]
 
 
 def _params():

@@ -9,6 +9,7 @@ import pytest
 import pdl_b200 as P
 from pdl_b200 import types as T, ufunc
 from parity import ALL_TYPES, INT_TYPES, assert_same, both, rand_array
+from replay import ulp_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -333,6 +334,40 @@ def test_divide_sqrt_fast_path_and_specials(engines, t):
         (ga, oa), (gb, ob) = both(engines, a2, t, True), both(engines, b2, t, True)
         assert_same(f"divide-specials-bad-{T.NAMES[t]}", P.run_biop("divide", ga, gb), P.run_biop("divide", oa, ob))
         assert_same(f"sqrt-specials-bad-{T.NAMES[t]}", P.run_ufunc("sqrt", ga), P.run_ufunc("sqrt", oa))
+
+
+@pytest.mark.parametrize("t", [T.CF, T.CD], ids=lambda t: T.NAMES[t])
+def test_complex_arithmetic(engines, t):
+    """plus minus mult divide on complex float / double: the device restatement of gcc's inline multiply and of
+    libgcc's __divsc3 / __divdc3 (scaled Smith) against the oracle, which is built by the reference's own compiler.
+    Magnitudes spread over the whole exponent range so that every scaling branch and the Annex G recovery of
+    infinities are reached; NaN parts must be NaN on both sides, everything else bit for bit."""
+    rng = np.random.default_rng(1480 + t)
+    rt = np.float32 if t == T.CF else np.float64
+    n = 300_007
+    emax = 36 if t == T.CF else 300
+
+    def parts():
+        v = rng.standard_normal(n) * 10.0 ** rng.integers(-emax, emax + 1, size=n)
+        v[rng.random(n) < 0.02] = 0.0
+        sp = rng.random(n) < 0.01
+        v[sp] = rng.choice(np.array([np.inf, -np.inf, np.nan, -0.0, np.finfo(rt).tiny / 8, np.finfo(rt).max]), size=int(sp.sum()))
+        return v.astype(rt)
+    with np.errstate(all="ignore"):
+        a = (parts() + 1j * parts()).astype(T.NP_DTYPE[t])
+        b = (parts() + 1j * parts()).astype(T.NP_DTYPE[t])
+    for op in ("plus", "minus", "mult", "divide"):
+        (ga, oa), (gb, ob) = both(engines, a, t), both(engines, b, t)
+        g, w = P.run_biop(op, ga, gb), P.run_biop(op, oa, ob)
+        assert g.type == w.type and g.dims == w.dims
+        assert ulp_diff(g.to_numpy().view(rt), w.to_numpy().view(rt)) == 0, f"{op}-{T.NAMES[t]}"
+        # BAD values, broadcasting over a dummy dim, a strided view
+        bad = np.array(T.DEFAULT_BAD[t]).astype(T.NP_DTYPE[t])
+        a2 = a[:3000].copy().reshape(30, 100)
+        a2[rng.random(a2.shape) < 0.05] = bad
+        (ga, oa), (gb, ob) = both(engines, a2, t, True), both(engines, b[:100], t)
+        g, w = P.run_biop(op, ga.slice("-1:0:-1,:"), gb), P.run_biop(op, oa.slice("-1:0:-1,:"), ob)
+        assert g.badflag == w.badflag and ulp_diff(g.to_numpy().view(rt), w.to_numpy().view(rt)) == 0, f"{op}-{T.NAMES[t]}-bad"
 
 
 @pytest.mark.parametrize("t", [T.B, T.S, T.L, T.LL, T.F, T.D], ids=lambda t: T.NAMES[t])
