@@ -693,7 +693,9 @@ def test_cabi_error_returns_on_device(cuda_engine):
     assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EUNSUPPORTED
     tr = desc("plus", [a, a, o]); tr.op = 49
     assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EINVAL and b"unknown op" in err.value
-    tr = desc("plus", [a, a, o]); tr.datatype = 12
+    tr = desc("plus", [a, a, o]); tr.datatype = 11            # long double: x87 80-bit, no device representation
+    assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EUNSUPPORTED and b"no device representation" in err.value
+    tr = desc("sqrt", [a, o]); tr.datatype = 12               # complex float is on the device path for + - * / only
     assert lib.pdlb200_readdata(C.byref(tr), err, 512) == _abi.EUNSUPPORTED and b"no device representation" in err.value
     # and the engine turns them into PDLError for the host mirror
     with pytest.raises(P.PDLError):
