@@ -37,7 +37,7 @@ def _default_incs(dims: Sequence[int]) -> list[int]:
 class PDL:
     """Device-resident ndarray.  dims[0] is the fastest-varying dim, as in PDL."""
 
-    __slots__ = ("engine", "_store", "datatype", "dims", "dimincs", "offs", "badflag",
+    __slots__ = ("engine", "_store", "datatype", "dims", "dimincs", "offs", "_bf",
                  "_badvalue", "_inplace", "_null", "_flowing", "_pending")
 
     def __init__(self, engine: Engine, store: Store | None, datatype: int, dims, dimincs=None,
@@ -50,6 +50,7 @@ class PDL:
         self.dims = [int(d) for d in dims]
         self.dimincs = [int(i) for i in (dimincs if dimincs is not None else _default_incs(self.dims))]
         self.offs = int(offs)
+        self._bf = False
         self.badflag = bool(badflag)
         self._badvalue = badvalue
         self._inplace = False
@@ -84,6 +85,21 @@ class PDL:
         p._null = True
         return p
 
+    # ---- bad state: per ndarray in the reference, but propagated through the vaffine family by
+    # pdl_propagate_badflag_dir (pdlapi.c:28-36, make_trans_mutual :806-808): a view and its parent are the same
+    # data, so the state lives with the shared buffer.  `x.slice(...).inplace().setvaltobad(0)` flags x too.
+    @property
+    def badflag(self) -> bool:
+        st = self._store
+        return self._bf or (st is not None and st.bad)
+
+    @badflag.setter
+    def badflag(self, flag) -> None:
+        self._bf = bool(flag)
+        st = self._store
+        if st is not None:
+            st.bad = bool(flag)
+
     # ---- dataflow: deferred readdata (lib/PDL/Core/pdlapi.c:781-801,890) ---------------
     @property
     def store(self):
@@ -116,6 +132,7 @@ class PDL:
         for d in self.dims:
             n *= d
         self._store = self.engine.alloc(n * T.SIZE[self.datatype])
+        self._store.bad = self._bf
         from .trans import run_op
         run_op(name, ins, [self])
 

@@ -26,10 +26,11 @@ class Store:
     """One device allocation (the reference's pdl.datasv / pdl.data, pdlapi.c:172-209).  `free` (set by the engine
     that allocated it) hands the block back when the last ndarray that views it goes away."""
 
-    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "_free", "__weakref__")
+    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "_free", "bad", "__weakref__")
 
     def __init__(self, engine, handle, ptr, nbytes, keep=None, free=None):
         self.engine, self.handle, self.ptr, self.nbytes, self._keep, self._free = engine, handle, ptr, nbytes, keep, free
+        self.bad = False      # the bad state of the DATA: shared by every view of this buffer (pdl_propagate_badflag_dir)
 
     def __del__(self):
         f = self._free

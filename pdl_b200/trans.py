@@ -156,7 +156,11 @@ def as_pdl(x, engine: Engine | None = None) -> PDL:
                 if len(_SCALARS) >= 512:
                     _SCALARS.clear()
                 _SCALARS[key] = p
-        return p._view(p.dims, p.dimincs, p.offs)       # a fresh ndarray object over the same bytes (flags are per object)
+        # a fresh ndarray object over the same bytes, behind its OWN Store record: the bad state lives with the Store, and
+        # a caller flagging its scalar must not flag everybody else's
+        from .engine import Store
+        st = p.store
+        return PDL(engine, Store(engine, None, st.ptr, st.nbytes, keep=st), p.datatype, p.dims, p.dimincs, p.offs)
     if isinstance(x, (list, tuple, np.ndarray)):
         from .core import pdl
         return pdl(x, engine=engine)

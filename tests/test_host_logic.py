@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import pdl_b200 as P
-from pdl_b200 import types as T, ufunc, ops
+from pdl_b200 import types as T, ufunc, ops, bad
 from pdl_b200.trans import transtype_select, SPECS, par_type
 
 
@@ -171,3 +171,21 @@ def test_flowing_defers_readdata_and_fuses_into_sumover(oracle_engine):
     # the flag applies to the NEXT operation only
     f = a.flowing()
     assert (f * b).is_pending() and not (a * b).is_pending()
+
+
+def test_badflag_is_shared_by_views_and_parent(oracle_engine):
+    """A view and its parent are the same data: flagging through one is seen through the other (the reference
+    propagates the flag through the vaffine family, pdlapi.c:28-36; round-1 advisor finding)."""
+    e = oracle_engine
+    x = P.PDL.from_numpy(np.arange(12, dtype=np.float64).reshape(3, 4), T.D, e)
+    v = x.slice("0:2,(1)")
+    assert not x.badflag and not v.badflag
+    bad.setvaltobad(v.inplace(), 5.0)
+    assert v.badflag and x.badflag                       # the parent sees it
+    s = ufunc.sumover(x)                                 # ... and BAD-mode reductions run: 4+6+7 (5 is BAD)
+    assert s.badflag and s.to_numpy().tolist() == [6.0, 17.0, 38.0]
+    x.badflag = False
+    assert not v.badflag
+    # scalars come from a cache of device ndarrays: flagging one use must not flag the next
+    a = P.as_pdl(7, e); a.badflag = True
+    assert not P.as_pdl(7, e).badflag
