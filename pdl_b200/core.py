@@ -91,7 +91,7 @@ class PDL:
     @property
     def badflag(self) -> bool:
         st = self._store
-        return self._bf or (st is not None and st.bad)
+        return st.bad if st is not None else self._bf
 
     @badflag.setter
     def badflag(self, flag) -> None:
