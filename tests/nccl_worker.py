@@ -76,7 +76,7 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     if use_peer:
-        assert comm._peer["epoch"] >= 20, "the peer-memory path was not the one that ran"
+        assert comm._peer["epoch"] >= 10, "the peer-memory path was not the one that ran"   # (records beyond a mailbox go by NCCL)
     print(f"rank {rank}: {checked} sharded-reduction checks ok ({'peer-memory exchange' if use_peer else 'nccl all-gather'})")
 
 
