@@ -341,13 +341,24 @@ template <class T, bool ISMAX> struct RMinMaxInt {
     const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
     int32_t nbad = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint32_t g = w[i];
-      if constexpr (BADK == 1) { const uint32_t m = swar_eq_mask<T>(g, badw, nbad); g = (g & ~m) | (identw & m); }
-      x.pk = pick_packed(x.pk, g);
+    if constexpr (BADK == 3) {
+      // the badvalue IS this reducer's identity (the default badvalues are the type extremes: minimum of an unsigned
+      // row, maximum of a signed one): BAD lanes cannot win, so no mask — only "was there a good lane at all"
+      int32_t good = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { x.pk = pick_packed(x.pk, w[i]); good |= (w[i] != badw); }
+      x.any |= good;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        uint32_t g = w[i];
+        if constexpr (BADK == 1) { const uint32_t m = swar_eq_mask<T>(g, badw, nbad); g = (g & ~m) | (identw & m); }
+        x.pk = pick_packed(x.pk, g);
+      }
+      x.any |= (nbad != (int32_t)(16 / sizeof(T)));
     }
-    x.any |= (nbad != (int32_t)(16 / sizeof(T)));
   }
+  static constexpr bool kBadIdentity = kPack;   // rd_row may pick BADK 3 when the badvalue equals identity()
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) {
     Acc x; x.cur = l.cur; x.any = l.any; x.pad = 0; x.pad2 = 0;
     if constexpr (kPack) {
@@ -474,9 +485,12 @@ template <class T, bool GOOD> struct RCount {
 // ---- row walk -------------------------------------------------------------------
 // BADK: 0 = no BAD test (good-mode code path), 1 = BAD iff v == badvalue, 2 = BAD iff v is NaN
 // (per-ndarray NaN badvalue).  Hoisted to a template so the hot loop pays one compare at most.
+template <class R, class = void> struct rd_kbadident { static constexpr bool value = false; };
+template <class R> struct rd_kbadident<R, std::void_t<decltype(R::kBadIdentity)>> { static constexpr bool value = R::kBadIdentity; };
+
 template <class R, class T, int BADK>
 __device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad) {
-  if constexpr (BADK == 1) { if (v == abad) return; }
+  if constexpr (BADK == 1 || BADK == 3) { if (v == abad) return; }
   if constexpr (BADK == 2) { if (t_isnan(v)) return; }
   R::lpush(loc, v, rel);
 }
@@ -539,6 +553,10 @@ template <class R, class T, bool BAD>
 __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64_t lo, int64_t hi, int64_t inc,
                                        int lane, int width, T abad, bool abadnan) {
   if constexpr (!BAD) rd_row_k<R, T, 0>(loc, row, lo, hi, inc, lane, width, abad);
+  else if constexpr (rd_kbadident<R>::value) {
+    if (abad == R::identity()) rd_row_k<R, T, 3>(loc, row, lo, hi, inc, lane, width, abad);
+    else rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad);
+  }
   else if constexpr (tt<T>::is_int) rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad);
   else { if (abadnan) rd_row_k<R, T, 2>(loc, row, lo, hi, inc, lane, width, abad);
          else rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad); }
@@ -736,27 +754,35 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
   }
 }
 
-// second stage: one warp per row merges that row's partials
+// second stage: merges each row's partials — one warp per row, or (few rows with many partials each: the whole-array
+// wrappers) one CTA per row, so that ~1200 partials are not walked by a single warp
 template <class R, class T, class O, bool BAD>
 __global__ void __launch_bounds__(RD_THREADS)
-reduce_finish_kernel(const __grid_constant__ RdPlan p) {
+reduce_finish_kernel(const __grid_constant__ RdPlan p, const int cta_per_row) {
   using Acc = typename R::Acc;
-  const int lane = threadIdx.x & 31;
-  int64_t row = (int64_t)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
-  const int64_t row_step = (int64_t)gridDim.x * (RD_THREADS / 32);
+  __shared__ Acc smem[RD_THREADS / 32 + 1];
+  const int lane = cta_per_row ? threadIdx.x : (threadIdx.x & 31), width = cta_per_row ? RD_THREADS : 32;
+  int64_t row = cta_per_row ? blockIdx.x : (int64_t)blockIdx.x * (RD_THREADS / 32) + (threadIdx.x >> 5);
+  const int64_t row_step = cta_per_row ? gridDim.x : (int64_t)gridDim.x * (RD_THREADS / 32);
   for (; row < p.nrows; row += row_step) {
     int64_t oa, ob;
     rd_row_offsets(p, row, oa, ob);
     Acc acc = R::init();
     const Acc *part = reinterpret_cast<const Acc *>(p.partial) + row * p.nchunks;
-    for (int c = lane; c < p.nchunks; c += 32) acc = R::merge(acc, part[c]);
+    for (int c = lane; c < p.nchunks; c += width) acc = R::merge(acc, part[c]);
+    if (cta_per_row) acc = rd_group_reduce<R, 2>(acc, smem);
+    else {
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
+      for (int m = 16; m >= 1; m >>= 1) acc = R::merge(acc, shfl_xor_acc(acc, m));
+    }
     O *out = reinterpret_cast<O *>(p.b) + ob;
     if constexpr (R::kPrefix) {
       if (acc.z != RD_NOIDX) {
         const T *rp = reinterpret_cast<const T *>(p.a) + oa;
-        const O v = rd_prod_prefix<R, T, O, BAD, 1>(rp, acc.z, p.inc_n, lane, 32, from_bits<T>(p.abad), p.abadnan != 0, nullptr);
+        O v;
+        if (cta_per_row) v = rd_prod_prefix<R, T, O, BAD, 2>(rp, acc.z, p.inc_n, lane, width, from_bits<T>(p.abad), p.abadnan != 0,
+                                                             reinterpret_cast<typename RProd<T, O>::Acc *>(smem));
+        else v = rd_prod_prefix<R, T, O, BAD, 1>(rp, acc.z, p.inc_n, lane, 32, from_bits<T>(p.abad), p.abadnan != 0, nullptr);
         if (lane == 0) *out = v;
         continue;
       }
@@ -784,11 +810,12 @@ int rd_launch_typed(const pdlb200_trans *t, const char *name, const Err &E) {
   note_launch(name);
   PDLB200_CUDA_OK(cudaGetLastError(), E);
   if (p.nchunks > 1) {
-    int64_t g = (p.nrows + RD_THREADS / 32 - 1) / (RD_THREADS / 32);
+    const int cta_per_row = (p.nrows <= 64 && p.nchunks >= 64) ? 1 : 0;
+    int64_t g = cta_per_row ? p.nrows : (p.nrows + RD_THREADS / 32 - 1) / (RD_THREADS / 32);
     const int64_t cap = (int64_t)sm_count() * 8;
     if (g > cap) g = cap;
-    if (t->bvalflag) reduce_finish_kernel<R, T, O, true><<<(int)g, RD_THREADS, 0, s>>>(p);
-    else reduce_finish_kernel<R, T, O, false><<<(int)g, RD_THREADS, 0, s>>>(p);
+    if (t->bvalflag) reduce_finish_kernel<R, T, O, true><<<(int)g, RD_THREADS, 0, s>>>(p, cta_per_row);
+    else reduce_finish_kernel<R, T, O, false><<<(int)g, RD_THREADS, 0, s>>>(p, cta_per_row);
     note_launch("reduce_finish");
     PDLB200_CUDA_OK(cudaGetLastError(), E);
   }
