@@ -130,6 +130,11 @@ enum {
 #define PDLB200_MAXDIMS 16  /* broadcast dims carried per call (pdl_broadcast.ndims) */
 #define PDLB200_MAXPDLS 5   /* parameters per transformation on this path (minmaximum has 5) */
 
+/* pdlb200_trans.tflags */
+#define PDLB200_TRANS_DEFER_ANYBAD 1 /* `anybad` points to PINNED host memory (pdlb200_host_alloc): the call only
+                                      * enqueues the 4-byte copy of the flag and does NOT synchronise the stream; the
+                                      * int32 is valid once the stream has been synchronised past this call */
+
 /* pdlb200_par.flags */
 #define PDLB200_PAR_BADFLAG 1  /* pdl->state & PDL_BADVAL                  pdl.h.PL:560-561 */
 #define PDLB200_PAR_BADNAN  2  /* the parameter's badvalue is NaN          pdlcore.h:202-205 */
@@ -153,7 +158,7 @@ typedef struct pdlb200_trans {
   int32_t bvalflag;  /* trans->bvalflag: any input had PDL_BADVAL (pdlapi.c:760-766) */
   int32_t npdls;     /* vtable->npdls */
   int32_t ndims;     /* broadcast.ndims (0 allowed) */
-  int32_t reserved;
+  int32_t tflags;    /* PDLB200_TRANS_* (0 = the plain synchronous call) */
   int64_t dims[PDLB200_MAXDIMS];                    /* broadcast.dims */
   int64_t incs[PDLB200_MAXDIMS * PDLB200_MAXPDLS];  /* broadcast.incs[d*npdls + p], elements */
   /* Named ("real") dims.  reductions/scans: n_size = ind[0], inc_a_n = rinc[0],
@@ -167,8 +172,9 @@ typedef struct pdlb200_trans {
   double  param;     /* the OtherPars double of setvaltobad (value) / setbadtoval (newval): $COMP(...) */
   /* set{nan,inf,nonfinite}tobad mark their output BAD only if they wrote a BAD value (`if (flag)
    * $PDLSTATESETBAD(b)`, lib/PDL/Bad.pd:695-707).  Those three ops REQUIRE a host pointer here; the
-   * call synchronises the stream and stores 1/0.  minmaximum uses it the same way for "a row had no
-   * usable element" (Ufunc.pd:578-583).  Ignored by every other op. */
+   * call synchronises the stream and stores 1/0 (unless tflags has PDLB200_TRANS_DEFER_ANYBAD).  minmaximum
+   * uses it the same way for "a row had no usable element" (Ufunc.pd:578-583), and _n_ind for "a slot could not be
+   * filled".  Ignored by every other op. */
   int32_t *anybad;
 } pdlb200_trans;
 

@@ -33,7 +33,7 @@ class Trans(C.Structure):
         ("bvalflag", C.c_int32),
         ("npdls", C.c_int32),
         ("ndims", C.c_int32),
-        ("reserved", C.c_int32),
+        ("tflags", C.c_int32),
         ("dims", C.c_int64 * MAXDIMS),
         ("incs", C.c_int64 * (MAXDIMS * MAXPDLS)),
         ("ind", C.c_int64 * 4),
@@ -69,6 +69,7 @@ OPS = {
     "minimum_n_ind": 90, "maximum_n_ind": 91,
 }
 ABI_VERSION = 4
+TRANS_DEFER_ANYBAD = 1     # pdlb200_trans.tflags
 
 # every symbol include/pdlb200.h declares (tests check the .so exports them all)
 SYMBOLS = [

@@ -13,6 +13,10 @@ static int flagged(const pdlb200_trans *t, const char *name, const Err &E) {
   if (!flag) return E.fail(PDLB200_ECUDA, "%s: cannot allocate the flag word", pdlb200_op_name(t->op));
   PDLB200_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int), s), E);
   if (int rc = ew_launch_typed<Op, T, T, 1>(t, false, name, E, 0, flag)) return rc;
+  if (t->tflags & PDLB200_TRANS_DEFER_ANYBAD) {     // pinned destination: no host round trip inside the call
+    PDLB200_CUDA_OK(cudaMemcpyAsync(t->anybad, flag, sizeof(int), cudaMemcpyDeviceToHost, s), E);
+    return PDLB200_OK;
+  }
   int host = 0;
   PDLB200_CUDA_OK(cudaMemcpyAsync(&host, flag, sizeof(int), cudaMemcpyDeviceToHost, s), E);
   PDLB200_CUDA_OK(cudaStreamSynchronize(s), E);

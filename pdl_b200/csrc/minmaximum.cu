@@ -49,7 +49,8 @@ template <class T> struct MmxAcc {
 // always fires at least one of the two compares (it cannot equal both identities), so "saw a usable element"
 // is imn >= 0 || imx >= 0; if only one side fired, every usable element equals the other side's identity and
 // that extreme sits at the first usable element, which is where the side that did fire recorded its first hit.
-// About 8 ALU instructions per element (the kernel is ALU-pipe bound, not DRAM bound: 4 bytes per element).
+// About 8 ALU instructions per element — too many for 4 bytes per element at HBM rate, so the vector loop runs it
+// only behind mmx_vec_extremes' filter (≈ 2.5 instructions per element on the common path).
 template <class T> struct MmxLoc {
   T mn, mx; int imn, imx;
   __device__ __forceinline__ void init() {
@@ -119,6 +120,33 @@ __device__ __forceinline__ bool mmx_usable(T v, T abad) {
 }
 
 template <class T, bool CHK>
+__device__ __forceinline__ void mmx_vec_extremes(const Pack<T> &r, T abad, T &vmn, T &vmx) {
+  constexpr int VEC = 16 / sizeof(T);
+  if constexpr (tt<T>::is_int) {
+    constexpr T hi = tt<T>::is_uns ? T(~T(0)) : T((typename tt<T>::wide_u(1) << (sizeof(T) * 8 - 1)) - 1);
+    constexpr T lo = tt<T>::is_uns ? T(0) : T(-hi - 1);
+    vmn = hi; vmx = lo;
+#pragma unroll
+    for (int k = 0; k < VEC; k++) {
+      const T v = r.e[k];
+      const bool bad = CHK && v == abad;
+      const T a = bad ? hi : v, b = bad ? lo : v;
+      vmn = a < vmn ? a : vmn; vmx = b > vmx ? b : vmx;
+    }
+  } else {
+    T e[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; k++) { e[k] = r.e[k]; if (CHK && e[k] == abad) e[k] = T(NAN); }
+    vmn = vmx = e[0];
+#pragma unroll
+    for (int k = 1; k < VEC; k++) {
+      if constexpr (sizeof(T) == 4) { vmn = fminf(vmn, e[k]); vmx = fmaxf(vmx, e[k]); }
+      else { vmn = fmin(vmn, e[k]); vmx = fmax(vmx, e[k]); }
+    }
+  }
+}
+
+template <class T, bool CHK>
 __global__ void __launch_bounds__(256, 4) minmaximum_warp_kernel(const __grid_constant__ MmxPlan p) {
   const T abad = from_bits<T>(p.abad);
   const int lane = threadIdx.x & 31;
@@ -147,8 +175,16 @@ __global__ void __launch_bounds__(256, 4) minmaximum_warp_kernel(const __grid_co
         for (int u = 0; u < U; u++) {
           const int64_t j = v0 + u * 32 + lane;
           if (j < nvec) {
+            // filter: extremes of the whole 16-byte vector first (unusable elements replaced by values that cannot
+            // win: NaN for floats — min/max return the other operand —, the identities for integers); the exact
+            // per-element strict-compare update runs only when the vector can change an extreme, which after the
+            // first few vectors is rare (the number of record-setting elements of a row grows like log n)
+            T vmn, vmx;
+            mmx_vec_extremes<T, CHK>(ra[u], abad, vmn, vmx);
+            if (vmn < loc.mn || vmx > loc.mx) {
 #pragma unroll
-            for (int k = 0; k < VEC; k++) { const T v = ra[u].e[k]; loc.step(v, (int)(j * VEC + k), mmx_usable<T, CHK>(v, abad)); }
+              for (int k = 0; k < VEC; k++) { const T v = ra[u].e[k]; loc.step(v, (int)(j * VEC + k), mmx_usable<T, CHK>(v, abad)); }
+            }
           }
         }
       }
@@ -297,6 +333,10 @@ int launch_minmaximum(const pdlb200_trans *t, const Err &E) {
   }
   if (rc) return rc;
   if (may_flag) {
+    if (t->tflags & PDLB200_TRANS_DEFER_ANYBAD) {   // pinned destination: no host round trip inside the call
+      PDLB200_CUDA_OK(cudaMemcpyAsync(t->anybad, scratch(64, s), sizeof(int), cudaMemcpyDeviceToHost, s), E);
+      return PDLB200_OK;
+    }
     int host = 0;
     PDLB200_CUDA_OK(cudaMemcpyAsync(&host, scratch(64, s), sizeof(int), cudaMemcpyDeviceToHost, s), E);
     PDLB200_CUDA_OK(cudaStreamSynchronize(s), E);

@@ -246,9 +246,17 @@ __global__ void __launch_bounds__(256) scan_chunk_prefix_kernel(const __grid_con
   }
 }
 
+}  // namespace pdlb200
+#include "scan_onepass.cuh"
+namespace pdlb200 {
+
 template <class T, class O, bool PROD>
 static int scan_go(const ScPlan &p, cudaStream_t s, const char *name, const Err &E) {
   const int64_t cap = (int64_t)sm_count() * 8;
+  {
+    int rc = PDLB200_OK;
+    if (scan_onepass_try<T, O, PROD>(p, s, name, E, &rc)) return rc;
+  }
   // long rows that are not laid out column-wise: one warp per row
   const bool column = (p.nd >= 1) && (p.sa[0] == 1 || p.sa[0] == -1) && p.inc_a != 1 && p.dims[0] >= 32;
   // chunk length: a multiple of SC_CHUNK giving about one resident wave of warps (64 per SM) over all rows

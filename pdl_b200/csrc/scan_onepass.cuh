@@ -2,30 +2,34 @@
 // ndarray is the common case, lib/PDL/Ufunc.pd:120-141).  Ideal traffic: every element is read once and
 // written once (the three-pass chunked path reads it twice).
 //
-// One persistent CTA per SM, 14 warps with fixed roles around a ring of OP_SLOTS shared-memory tiles of 48 KB:
+// One persistent CTA per SM, 23 warps with fixed roles around a ring of OP_SLOTS shared-memory tiles of 40 KB;
+// tiles move in AND out with bulk-async copies (cp.async.bulk, UBLKCP), the scan happens in place in shared memory:
 //   producer (1 thread)  takes the next tile number from a global counter (tiles are handed out in the order
 //                        CTAs actually run, so a look-back never waits on a CTA that is not resident) and
-//                        fills the slot with ONE bulk-async copy (cp.async.bulk, UBLKCP) armed on an mbarrier;
-//   aggregators (4 warps) run AHEAD of the scanners: per-segment totals of the tile from shared memory, the
-//                        tile aggregate, and the tile's descriptor {status A, aggregate} published to global;
+//                        fills the slot with ONE bulk copy armed on an mbarrier (expect_tx);
+//   aggregators (4 warps) run AHEAD of the scanners: per-segment totals of the tile, the tile aggregate, and
+//                        the tile's descriptor {status A, aggregate} published to global;
 //   prefix warp          decoupled look-back over the 32 preceding descriptors per round trip until it meets
 //                        an inclusive prefix (status P), then publishes {P, prefix+aggregate} — before the
 //                        tile itself is scanned, so successors are released early;
-//   scanners (8 warps)   one segment each: carry = tile prefix + totals of the segments before it, then the
-//                        in-lane / warp-shuffle scan of 128-bit vectors from shared memory, 128-bit stores.
+//   scanners (16 warps)  one segment each; every LANE owns OP_VPL consecutive 16-byte vectors (5: an odd lane
+//                        stride of 80 bytes keeps the 128-bit shared-memory accesses bank-conflict free): a
+//                        serial in-lane scan, ONE warp shuffle scan of the lane totals per tile, results written
+//                        back in place (≈ 0.1 warp instructions per element);
+//   storer (1 thread)    ONE bulk copy shared -> global per tile; the slot is free again once it has been read.
 // Descriptors are one 64-bit word {status, value} for 4-byte results and one 16-byte vector {status, value}
 // for 8-byte results; the array and the counter are cleared by one memset per launch.
 #pragma once
 
 namespace pdlb200 {
 
-constexpr int OP_TILE_BYTES = 49152;
-constexpr int OP_SLOTS = 4;
-constexpr int OP_NSCAN = 8;
+constexpr int OP_NSCAN = 16;
 constexpr int OP_NAGG = 4;
-constexpr int OP_THREADS = (OP_NSCAN + OP_NAGG + 2) * 32;
-constexpr int OP_SEG_VECS = OP_TILE_BYTES / OP_NSCAN / 16;      // 384 vectors of 16 bytes per segment
-constexpr int OP_SEG_STEPS = OP_SEG_VECS / 32;                  // 12 per lane
+constexpr int OP_VPL = 5;                                        // 16-byte vectors per scanner lane
+constexpr int OP_SEG_VECS = 32 * OP_VPL;                         // 160 vectors per segment
+constexpr int OP_TILE_BYTES = OP_NSCAN * OP_SEG_VECS * 16;       // 40960
+constexpr int OP_SLOTS = 5;
+constexpr int OP_THREADS = (OP_NSCAN + OP_NAGG + 3) * 32;
 
 struct OpPlan {
   const char *a; char *b;
@@ -52,6 +56,11 @@ __device__ __forceinline__ void op_mbar_wait(uint64_t *bar, unsigned parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra OPD_%=;\nbra OPW_%=;\nOPD_%=:\n}\n"
       :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void op_bulk_store(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+               :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 __device__ __forceinline__ void op_bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -89,26 +98,30 @@ template <class O> struct OpDesc<O, 8> {
   }
 };
 
-template <class T, class O, bool PROD>
+template <class T, class O, bool PROD, bool BAD>
 __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __grid_constant__ OpPlan p) {
   extern __shared__ __align__(128) unsigned char op_tiles[];
   __shared__ struct {
-    O segtot[OP_SLOTS][OP_NSCAN];
+    O segtot[OP_SLOTS][OP_NSCAN], segpre[OP_SLOTS][OP_NSCAN];
     O tagg[OP_SLOTS], tpre[OP_SLOTS];
-    long long stile[OP_SLOTS];
-    uint64_t full[OP_SLOTS], aggd[OP_SLOTS], pref[OP_SLOTS], empty[OP_SLOTS];
+    int stile[OP_SLOTS];
+    uint64_t full[OP_SLOTS], aggd[OP_SLOTS], pref[OP_SLOTS], scanned[OP_SLOTS], empty[OP_SLOTS];
   } c;
   constexpr int TE = OP_TILE_BYTES / (int)sizeof(T);
   constexpr int VEC = 16 / (int)sizeof(T);
   const T abad = from_bits<T>(p.abad);
   const O bbad = from_bits<O>(p.bbad);
   const O ident = PROD ? O(1) : O(0);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool badmode = p.badmode != 0, badnan = p.abadnan != 0;
+  const int lane = threadIdx.x & 31;
+  // broadcast from lane 0: tells the compiler the role (and every tile number below) is warp-uniform, so the
+  // shuffles in the role loops need no reconvergence bookkeeping
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const bool badnan = p.abadnan != 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < OP_SLOTS; s++) {
-      op_mbar_init(&c.full[s], 1); op_mbar_init(&c.aggd[s], 1); op_mbar_init(&c.pref[s], 1); op_mbar_init(&c.empty[s], OP_NSCAN);
+      op_mbar_init(&c.full[s], 1); op_mbar_init(&c.aggd[s], 1); op_mbar_init(&c.pref[s], 1);
+      op_mbar_init(&c.scanned[s], OP_NSCAN); op_mbar_init(&c.empty[s], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -117,29 +130,51 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
   if (wid == OP_NSCAN + OP_NAGG + 1) {
     // ---- producer ----
     if (lane != 0) return;
+    // the tile number is fetched one tile ahead, so the atomic's round trip is not in series with the slot wait
+    long long t = (long long)atomicAdd(p.counter, 1u);
     for (unsigned it = 0;; it++) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
       if (it >= OP_SLOTS) op_mbar_wait(&c.empty[s], (u - 1) & 1);
-      const long long t = (long long)atomicAdd(p.counter, 1u);
       if (t >= p.ntiles) { c.stile[s] = -1; op_mbar_arrive(&c.full[s]); return; }
-      c.stile[s] = t;
+      c.stile[s] = (int)t;
       const int64_t row = t / p.tpr, j = t - row * p.tpr;
       const int64_t left = p.n - j * TE;
       const unsigned bytes = (unsigned)((left < TE ? left : TE) * (int64_t)sizeof(T));
       op_mbar_expect_tx(&c.full[s], bytes);
       op_bulk_load(op_tiles + (size_t)s * OP_TILE_BYTES, p.a + (row * p.sa + j * TE) * (int64_t)sizeof(T), bytes, &c.full[s]);
+      t = (long long)atomicAdd(p.counter, 1u);
     }
   }
 
+  if (wid == OP_NSCAN + OP_NAGG + 2) {
+    // ---- storer ----
+    if (lane != 0) return;
+    for (unsigned it = 0;; it++) {
+      const int s = it % OP_SLOTS;
+      const unsigned u = it / OP_SLOTS;
+      op_mbar_wait(&c.scanned[s], u & 1);
+      const long long t = c.stile[s];
+      if (t < 0) break;
+      const int64_t row = t / p.tpr, j = t - row * p.tpr;
+      const int64_t left = p.n - j * TE;
+      const unsigned bytes = (unsigned)((left < TE ? left : TE) * (int64_t)sizeof(O));
+      op_bulk_store(p.b + (row * p.sb + j * TE) * (int64_t)sizeof(O), op_tiles + (size_t)s * OP_TILE_BYTES, bytes);
+      asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // the slot has been read: reusable
+      op_mbar_arrive(&c.empty[s]);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    return;
+  }
+
   if (wid >= OP_NSCAN && wid < OP_NSCAN + OP_NAGG) {
-    // ---- aggregators: two segments per warp ----
+    // ---- aggregators: OP_NSCAN / OP_NAGG segments per warp ----
     const int aw = wid - OP_NSCAN;
     for (unsigned it = 0;; it++) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
       op_mbar_wait(&c.full[s], u & 1);
-      const long long t = c.stile[s];
+      const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
       if (t < 0) { if (aw == 0 && lane == 0) op_mbar_arrive(&c.aggd[s]); return; }
       const int64_t j = t % p.tpr;
       const int64_t left = p.n - j * TE;
@@ -148,18 +183,21 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
 #pragma unroll
       for (int h = 0; h < OP_NSCAN / OP_NAGG; h++) {
         const int seg = aw * (OP_NSCAN / OP_NAGG) + h;
-        O tot[4] = {ident, ident, ident, ident};
+        O tot[OP_VPL];
 #pragma unroll
-        for (int k = 0; k < OP_SEG_STEPS; k++) {
+        for (int k = 0; k < OP_VPL; k++) {
+          tot[k] = ident;
           const int v = seg * OP_SEG_VECS + k * 32 + lane;
           if (v < nvec) {
             Pack<T> in; in.q = tv[v];
 #pragma unroll
             for (int e = 0; e < VEC; e++)
-              if (!(badmode && is_bad(in.e[e], abad, badnan))) tot[k & 3] = scan_op<O, PROD>(tot[k & 3], (O)in.e[e]);
+              if (!(BAD && is_bad(in.e[e], abad, badnan))) tot[k] = scan_op<O, PROD>(tot[k], (O)in.e[e]);
           }
         }
-        O r = scan_op<O, PROD>(scan_op<O, PROD>(tot[0], tot[1]), scan_op<O, PROD>(tot[2], tot[3]));
+        O r = tot[0];
+#pragma unroll
+        for (int k = 1; k < OP_VPL; k++) r = scan_op<O, PROD>(r, tot[k]);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) r = scan_op<O, PROD>(r, shfl_xor_t(r, d));
         if (lane == 0) c.segtot[s][seg] = r;
@@ -168,7 +206,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
       if (aw == 0 && lane == 0) {
         O agg = ident;
 #pragma unroll
-        for (int sg = 0; sg < OP_NSCAN; sg++) agg = scan_op<O, PROD>(agg, c.segtot[s][sg]);
+        for (int sg = 0; sg < OP_NSCAN; sg++) { c.segpre[s][sg] = agg; agg = scan_op<O, PROD>(agg, c.segtot[s][sg]); }
         c.tagg[s] = agg;
         OpDesc<O>::put(p.desc, t, j == 0 ? 2u : 1u, agg);
         op_mbar_arrive(&c.aggd[s]);
@@ -182,13 +220,13 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
       op_mbar_wait(&c.aggd[s], u & 1);
-      const long long t = c.stile[s];
+      const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
       if (t < 0) { if (lane == 0) op_mbar_arrive(&c.pref[s]); return; }
       const int64_t j = t % p.tpr;
       O excl = ident;
       if (j > 0) {
         const int64_t lowest = t - j;             // first tile of this row: always published as P
-        int64_t pos = t - 1;
+        int64_t pos = (int64_t)t - 1;
         long long t0 = 0; bool timing = false;
         for (;;) {
           const int64_t idx = pos - lane;
@@ -203,7 +241,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
             // a predecessor has not published yet: it is resident (tiles are taken in execution order)
             if (!timing) { timing = true; t0 = clock64(); }
             else if (clock64() - t0 > 20000000000ll) __trap();     // ≈10 s: fail loudly instead of hanging the GPU
-            __nanosleep(40);
+            __nanosleep(20);
             continue;
           }
           O x = (valid && lane <= np) ? v : ident;
@@ -223,58 +261,62 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
     }
   }
 
-  // ---- scanners: warp `wid` owns segment `wid` of every tile ----
+  // ---- scanners: warp `wid` owns segment `wid` of every tile, lane owns OP_VPL consecutive vectors of it ----
   for (unsigned it = 0;; it++) {
     const int s = it % OP_SLOTS;
     const unsigned u = it / OP_SLOTS;
     op_mbar_wait(&c.pref[s], u & 1);
     op_mbar_wait(&c.full[s], u & 1);                // already complete: makes the bulk copy's writes visible to this warp
-    const long long t = c.stile[s];
-    if (t < 0) return;
-    const int64_t row = t / p.tpr, j = t - row * p.tpr;
+    const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
+    if (t < 0) { if (lane == 0) op_mbar_arrive(&c.scanned[s]); return; }
+    const int64_t j = t % p.tpr;
     const int64_t left = p.n - j * TE;
     const int nvec = (int)((left < TE ? left : TE) / VEC);
-    O carry = c.tpre[s];
-    for (int sg = 0; sg < wid; sg++) carry = scan_op<O, PROD>(carry, c.segtot[s][sg]);
-    const uint4 *tv = reinterpret_cast<const uint4 *>(op_tiles + (size_t)s * OP_TILE_BYTES);
-    uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<O *>(p.b) + row * p.sb + j * TE);
-#pragma unroll 4
-    for (int k = 0; k < OP_SEG_STEPS; k++) {
-      const int v0 = wid * OP_SEG_VECS + k * 32;
-      if (v0 >= nvec) break;
-      const int v = v0 + lane;
-      const bool inr = v < nvec;
-      Pack<T> in;
-      if (inr) in.q = tv[v];
-      O x[VEC]; bool bd[VEC];
+    const int v0 = wid * OP_SEG_VECS + lane * OP_VPL;
+    if (wid * OP_SEG_VECS < nvec) {
+      const O carry = scan_op<O, PROD>(c.tpre[s], c.segpre[s][wid]);
+      uint4 *tv = reinterpret_cast<uint4 *>(op_tiles + (size_t)s * OP_TILE_BYTES);
+      Pack<T> in[OP_VPL];
+#pragma unroll
+      for (int k = 0; k < OP_VPL; k++) if (v0 + k < nvec) in[k].q = tv[v0 + k];
+      O x[OP_VPL][VEC];
+      unsigned bdm = 0;
       O run = ident;
 #pragma unroll
-      for (int e = 0; e < VEC; e++) {
-        const T val = inr ? in.e[e] : T(0);
-        bd[e] = inr && badmode && is_bad(val, abad, badnan);
-        if (inr && !bd[e]) run = scan_op<O, PROD>(run, (O)val);
-        x[e] = run;
+      for (int k = 0; k < OP_VPL; k++) {
+        const bool inr = v0 + k < nvec;
+#pragma unroll
+        for (int e = 0; e < VEC; e++) {
+          const T val = inr ? in[k].e[e] : T(0);
+          const bool bd = BAD && inr && is_bad(val, abad, badnan);
+          if (BAD && bd) bdm |= 1u << (k * VEC + e);
+          if (inr && !bd) run = scan_op<O, PROD>(run, (O)val);
+          x[k][e] = run;
+        }
       }
-      O pre = run;
+      O pre = run;                                    // inclusive scan of the lane totals
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const O y = shfl_up_t(pre, d);
         if (lane >= d) pre = scan_op<O, PROD>(y, pre);
       }
-      const O warp_total = shfl_idx_t(pre, 31);
       O excl = shfl_up_t(pre, 1);
       if (lane == 0) excl = ident;
       const O base = scan_op<O, PROD>(carry, excl);
-      if (inr) {
-        Pack<O> out;
 #pragma unroll
-        for (int e = 0; e < VEC; e++) out.e[e] = bd[e] ? bbad : scan_op<O, PROD>(base, x[e]);
-        dst[v] = out.q;
+      for (int k = 0; k < OP_VPL; k++) {
+        if (v0 + k < nvec) {
+          Pack<O> out;
+#pragma unroll
+          for (int e = 0; e < VEC; e++)
+            out.e[e] = (BAD && ((bdm >> (k * VEC + e)) & 1u)) ? bbad : scan_op<O, PROD>(base, x[k][e]);
+          tv[v0 + k] = out.q;
+        }
       }
-      carry = scan_op<O, PROD>(carry, warp_total);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the bulk store
     }
     __syncwarp();
-    if (lane == 0) op_mbar_arrive(&c.empty[s]);
+    if (lane == 0) op_mbar_arrive(&c.scanned[s]);
   }
 }
 
@@ -308,12 +350,15 @@ static bool scan_onepass_try(const ScPlan &p, cudaStream_t s, const char *name, 
     q.counter = (unsigned int *)(scr + dbytes);
     if (cudaMemsetAsync(scr, 0, dbytes + 16, s) != cudaSuccess) { *rc = E.fail(PDLB200_ECUDA, "%s: memset failed", name); return true; }
     static const bool attr = [] {
-      return cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      return cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  OP_SLOTS * OP_TILE_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   OP_SLOTS * OP_TILE_BYTES) == cudaSuccess;
     }();
     if (!attr) { cudaGetLastError(); return false; }
     const int64_t g = ntiles < sm_count() ? ntiles : sm_count();
-    scan_onepass_kernel<T, O, PROD><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
+    if (q.badmode) scan_onepass_kernel<T, O, PROD, true><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
+    else scan_onepass_kernel<T, O, PROD, false><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
     note_launch(name);
     cudaError_t e = cudaGetLastError();
     *rc = e == cudaSuccess ? PDLB200_OK : E.fail(PDLB200_ECUDA, "%s: %s", name, cudaGetErrorString(e));

@@ -26,11 +26,22 @@ class Store:
     """One device allocation (the reference's pdl.datasv / pdl.data, pdlapi.c:172-209).  `free` (set by the engine
     that allocated it) hands the block back when the last ndarray that views it goes away."""
 
-    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "_free", "bad", "__weakref__")
+    __slots__ = ("engine", "handle", "ptr", "nbytes", "_keep", "_free", "_bad", "_pend", "__weakref__")
 
     def __init__(self, engine, handle, ptr, nbytes, keep=None, free=None):
         self.engine, self.handle, self.ptr, self.nbytes, self._keep, self._free = engine, handle, ptr, nbytes, keep, free
-        self.bad = False      # the bad state of the DATA: shared by every view of this buffer (pdl_propagate_badflag_dir)
+        self._bad = False     # the bad state of the DATA: shared by every view of this buffer (pdl_propagate_badflag_dir)
+        self._pend = None     # slot of a data-dependent flag still in flight (FlagRing), OR-ed in when first asked for
+
+    @property
+    def bad(self) -> bool:
+        if self._pend is not None:
+            self.engine.flag_ring.resolve()
+        return self._bad
+
+    @bad.setter
+    def bad(self, v: bool) -> None:
+        self._bad, self._pend = bool(v), None
 
     def __del__(self):
         f = self._free
@@ -39,6 +50,51 @@ class Store:
                 f(self.ptr, self.nbytes)
             except Exception:  # interpreter shutdown: the library may already be gone
                 pass
+
+
+class FlagRing:
+    """Data-dependent output badflags without a host round trip per op (`if (flag) $PDLSTATESETBAD(...)`,
+    lib/PDL/Bad.pd:695-707, Ufunc.pd:578-583): the op copies its flag word into one of 1024 pinned int32 slots
+    (PDLB200_TRANS_DEFER_ANYBAD) and the output Stores remember the slot; the first question about their bad
+    state synchronises the stream once and settles every flag in flight."""
+
+    SLOTS = 1024
+
+    def __init__(self, engine):
+        import weakref
+        self._ref = weakref.ref
+        self.engine = engine
+        self.page = engine.lib.pdlb200_host_alloc(4 * self.SLOTS)
+        if not self.page:
+            raise PDLError("pdl_b200: cannot allocate the pinned flag page")
+        self.arr = (C.c_int32 * self.SLOTS).from_address(self.page)
+        self.next, self.pending = 0, {}
+
+    def take(self):
+        """-> (slot, POINTER(c_int32)) for the next deferred call."""
+        slot = self.next
+        self.next = (slot + 1) % self.SLOTS
+        if slot in self.pending:
+            self.resolve()
+        self.arr[slot] = 0
+        return slot, C.cast(self.page + 4 * slot, C.POINTER(C.c_int32))
+
+    def attach(self, slot, stores) -> None:
+        for s in stores:
+            s._pend = slot
+        self.pending[slot] = [self._ref(s) for s in stores]
+
+    def resolve(self) -> None:
+        self.engine.sync()
+        pending, self.pending = self.pending, {}
+        for slot, refs in pending.items():
+            v = self.arr[slot]
+            for r in refs:
+                s = r()
+                if s is not None and s._pend == slot:
+                    s._pend = None
+                    if v:
+                        s._bad = True
 
 
 class Engine:
@@ -81,6 +137,13 @@ class CudaEngine(Engine):
         self._check(self.lib.pdlb200_set_device(device, self._err, 512))
         self.stream = None  # legacy default stream: ordered with torch's default stream
         self._dev_alloc, self._dev_free = self.lib.pdlb200_dev_alloc, self.lib.pdlb200_dev_free
+        self._flag_ring = None
+
+    @property
+    def flag_ring(self) -> FlagRing:
+        if self._flag_ring is None:
+            self._flag_ring = FlagRing(self)
+        return self._flag_ring
 
     def _check(self, rc: int) -> None:
         if rc != 0:

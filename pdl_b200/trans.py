@@ -283,6 +283,31 @@ def _check_output_dims(p: PDL, realdims: int, bc: Broadcast, opname: str, pname:
 
 
 # ---- the descriptor ---------------------------------------------------------------------------
+_FLAG_DEFERRABLE = ("minmaximum", "setnantobad", "setinftobad", "setnonfinitetobad")   # ops honouring DEFER_ANYBAD
+
+
+def _readdata_flagged(engine, tr, name):
+    """One readdata of an op with a data-dependent output badflag.  -> the flag (0/1), or the FlagRing slot as
+    a 1-tuple when the engine defers the read-back (no stream synchronise inside the call)."""
+    ring = getattr(engine, "flag_ring", None) if name in _FLAG_DEFERRABLE else None
+    if ring is None:
+        engine.readdata(tr)
+        return int(tr._anybad.value)
+    slot, ptr = ring.take()
+    tr.anybad, tr.tflags = ptr, _abi.TRANS_DEFER_ANYBAD
+    engine.readdata(tr)
+    return (slot,)
+
+
+def _apply_flag(engine, flag, outs) -> None:
+    """`if (flag) $PDLSTATESETBAD(out)` for every output — now, or when the deferred flag is first needed."""
+    if isinstance(flag, tuple):
+        engine.flag_ring.attach(flag[0], [o.store for o in outs])
+    elif flag:
+        for o in outs:
+            o.badflag = True
+
+
 
 class Prepared:
     """A transformation whose descriptor is already filled in: calling it is ONE C-ABI call.
@@ -295,18 +320,20 @@ class Prepared:
         self.engine, self.trans, self.outputs, self._keep, self._flagged = engine, trans, outputs, keep, flagged
 
     def __call__(self):
-        self.engine.readdata(self.trans)
-        if self._flagged and self.trans._anybad.value:     # `if (flag) $PDLSTATESETBAD(...)` of the op's Code
-            for o in self.outputs:
-                o.badflag = True
+        if self._flagged:                                  # `if (flag) $PDLSTATESETBAD(...)` of the op's Code
+            _apply_flag(self.engine, _readdata_flagged(self.engine, self.trans, self._flagged), self.outputs)
+        else:
+            self.engine.readdata(self.trans)
         return self.outputs
 
 
 def _launch(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> int:
     """One readdata.  Returns the op's `flag` (ops with a data-dependent output badflag), else 0."""
     tr = _build_trans(spec, transtype, pdls, bc, named, bval)
+    if spec.name in _STATE_IFFLAG:
+        return _readdata_flagged(pdls[0].engine, tr, spec.name)
     pdls[0].engine.readdata(tr)
-    return int(tr._anybad.value) if spec.name in _STATE_IFFLAG else 0
+    return 0
 
 
 def _build_trans(spec: OpSpec, transtype: int, pdls: list, bc: Broadcast, named: dict, bval: bool) -> _abi.Trans:
@@ -396,12 +423,18 @@ def _replay(ent: _Cached, ins: list, outs: list, engine) -> list:
         if ent.bval or ent.force_bad:
             o.badflag = True
         res.append(o)
-    engine.readdata(ent.tr)
     name = ent.name
+    flag = 0
+    if ent.ifflag:
+        flag = _readdata_flagged(engine, ent.tr, name)
+    else:
+        engine.readdata(ent.tr)
     if name in _STATE_GOOD_UNLESS_FLAG:
         for o in res:
             o.badflag = False
-    if name in _STATE_SETBAD or (ent.ifflag and ent.tr._anybad.value):
+    if ent.ifflag and flag:
+        _apply_flag(engine, flag, res)
+    elif name in _STATE_SETBAD:
         for o in res:
             o.badflag = True
     elif name in _STATE_SETGOOD:
@@ -564,10 +597,13 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
             for o in placeholder[len(ins):]:
                 o.badflag = False
         return Prepared(engine, _build_trans(spec, transtype, placeholder, bc, named, bval), final_outs, placeholder,
-                        flagged=name in _STATE_IFFLAG)
+                        flagged=name if name in _STATE_IFFLAG else False)
     tr = _build_trans(spec, transtype, placeholder, bc, named, bval)
-    engine.readdata(tr)
-    flag = int(tr._anybad.value) if name in _STATE_IFFLAG else 0
+    flag = 0
+    if name in _STATE_IFFLAG:
+        flag = _readdata_flagged(engine, tr, name)
+    else:
+        engine.readdata(tr)
     if key is not None and not temps and all(a is b for a, b in zip(ins, ins_given)):
         # nothing was converted: the descriptor is reusable for every later call with the same key
         if len(_DESC_CACHE) >= 4096:
@@ -578,7 +614,9 @@ def run_op(name: str, inputs: list, outputs: list | None = None, _prepare: bool 
     if name in _STATE_GOOD_UNLESS_FLAG:
         for o in placeholder[len(ins):]:
             o.badflag = False
-    if name in _STATE_SETBAD or (name in _STATE_IFFLAG and flag):
+    if name in _STATE_IFFLAG and flag:
+        _apply_flag(engine, flag, placeholder[len(ins):])
+    elif name in _STATE_SETBAD:
         for o in placeholder[len(ins):]:
             o.badflag = True
     elif name in _STATE_SETGOOD:

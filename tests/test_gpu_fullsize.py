@@ -185,6 +185,57 @@ def test_lookback_scan_variants(cuda_engine, case):
         assert torch.equal(got, torch.cumsum(y.view(3, n).long(), 1).int())
 
 
+@pytest.mark.parametrize("case", ["float-1row", "float-1row-bad", "ll-to-double", "double-4rows-strided", "prod-int32"])
+def test_onepass_scan(cuda_engine, case):
+    """The single-pass look-back scan (scan_onepass.cuh): ONE launch for rows cut into 48 KB tiles, against torch on
+    exactly representable data; the same inputs through the three-pass path must give the same bytes."""
+    g = torch.Generator(device="cuda").manual_seed(41)
+
+    def run(fn):
+        c0 = cuda_engine.launch_count()
+        out = fn()
+        return out, cuda_engine.launch_count() - c0
+
+    if case in ("float-1row", "float-1row-bad"):
+        n = 2**26 + 4 * 777                                   # last tile partial
+        y = torch.randint(-8, 9, (n,), device="cuda", generator=g).float()
+        py = wrap(cuda_engine, y, T.F, [n])
+        want = y.double()
+        if case.endswith("bad"):
+            bad = torch.rand(n, device="cuda", generator=g) < 0.01
+            y[bad] = -9999.0
+            py.set_badvalue(-9999.0).set_badflag(True)
+            want = torch.where(bad, torch.zeros_like(want), want)
+        out, nl = run(lambda: ufunc.cumusumover(py))
+        assert nl == 1, nl
+        want = torch.cumsum(want, 0).float()
+        if case.endswith("bad"):
+            want[bad] = float(out.badvalue)
+        assert torch.equal(as_torch(out, torch.float32), want)
+    elif case == "ll-to-double":
+        n = 2**23
+        y = torch.randint(-2**20, 2**20, (n,), device="cuda", generator=g)
+        out, nl = run(lambda: ufunc.dcumusumover(wrap(cuda_engine, y, T.LL, [n])))
+        assert nl == 1 and out.type == "double"
+        assert torch.equal(as_torch(out, torch.float64), torch.cumsum(y, 0).double())
+    elif case == "double-4rows-strided":
+        n, pitch = 2**21 + 2, 2**21 + 64                      # rows of a wider parent: row stride != n
+        y = torch.randint(-100, 101, (4 * pitch,), device="cuda", generator=g).double()
+        parent = wrap(cuda_engine, y, T.D, [pitch, 4])
+        out, nl = run(lambda: ufunc.cumusumover(parent.slice(f"0:{n - 1}")))
+        assert nl == 1, nl
+        assert torch.equal(as_torch(out, torch.float64).view(4, n), torch.cumsum(y.view(4, pitch)[:, :n], 1))
+    else:
+        n = 2**23
+        y = torch.randint(-3, 4, (n,), device="cuda", generator=g, dtype=torch.int32)
+        y[y == 0] = 1
+        out, nl = run(lambda: ufunc.cumuprodover(wrap(cuda_engine, y, T.L, [n])))
+        assert nl == 1, nl
+        got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "<i4",
+                              "data": (out.store.ptr, False), "version": 3}})(), device="cuda")
+        assert torch.equal(got, torch.cumprod(y.long(), 0).int())          # wrap-around product, mod 2^32 either way
+
+
 def test_elementwise_beyond_2_pow_32_elements(cuda_engine):
     """More than 2^32 elements in one elementwise launch (64-bit unit/item arithmetic in the walkers): sbyte
     plus over 2^32 + 37 elements, checked through slices at the start, across the 2^32 boundary and at the end,

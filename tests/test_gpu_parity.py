@@ -551,6 +551,19 @@ def test_minmaximum(engines, t):
             assert_same(f"minmaximum-nan[{k}]-{T.NAMES[t]}", g, o)
         assert ufunc.minmaximum(ga)[0].badflag
         assert ufunc.minmax(ga) == ufunc.minmax(oa)
+        # the data-dependent flag travels through a pinned slot (PDLB200_TRANS_DEFER_ANYBAD): the call itself does not
+        # synchronise; the first question about the bad state settles it, for every output and every view
+        outs = ufunc.minmaximum(ga)
+        assert all(o.store._pend is not None for o in outs)
+        view = outs[2].slice("0:3")
+        assert view.badflag and all(o.store._pend is None for o in outs) and all(o.badflag for o in outs)
+        good = np.ascontiguousarray(a[:3])
+        good[np.isnan(good)] = 1.0
+        outs = ufunc.minmaximum(P.PDL.from_numpy(good, t, engines[0]))
+        assert outs[0].store._pend is not None and not outs[0].badflag and not outs[3].badflag
+        outs = ufunc.minmaximum(ga)
+        outs[0].badflag = False                            # an explicit setting wins over a flag still in flight
+        assert outs[0].store._pend is None and not outs[0].badflag and outs[1].badflag
 
 
 @pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])

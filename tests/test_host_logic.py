@@ -189,3 +189,43 @@ def test_badflag_is_shared_by_views_and_parent(oracle_engine):
     # scalars come from a cache of device ndarrays: flagging one use must not flag the next
     a = P.as_pdl(7, e); a.badflag = True
     assert not P.as_pdl(7, e).badflag
+
+
+def test_deferred_output_badflag_ring(oracle_engine, monkeypatch):
+    """FlagRing (engine.py): ops with a data-dependent output badflag (minmaximum, set*tobad) hand the C call a
+    pinned slot instead of synchronising; the output Stores settle it at the first question about their bad state.
+    Host logic only — the oracle engine stands in for the device and writes the slot synchronously."""
+    import ctypes as C
+    from pdl_b200 import engine as E
+
+    class _Lib:
+        def pdlb200_host_alloc(self, n):
+            self.buf = C.create_string_buffer(n)
+            return C.addressof(self.buf)
+
+    class _Dev:
+        lib, syncs = _Lib(), 0
+
+        def sync(self):
+            _Dev.syncs += 1
+
+    ring = E.FlagRing(_Dev())
+    monkeypatch.setattr(type(oracle_engine), "flag_ring", property(lambda self: ring), raising=False)
+    a = np.random.default_rng(3).random((4, 50)).astype(np.float32)
+    a[2, :] = np.nan                                         # a row without a usable element: outputs flagged BAD
+    ga = P.PDL.from_numpy(a, T.F, oracle_engine)
+    outs = ufunc.minmaximum(ga)
+    assert [o.store._pend for o in outs] == [0, 0, 0, 0] and _Dev.syncs == 0
+    outs2 = ufunc.minmaximum(P.PDL.from_numpy(np.nan_to_num(a, nan=1.0), T.F, oracle_engine))
+    assert outs2[0].store._pend == 1 and _Dev.syncs == 0
+    assert outs[3].slice("0:1").badflag and _Dev.syncs == 1   # one synchronise settles every flag in flight
+    assert all(o.store._pend is None for o in outs + outs2) and all(o.badflag for o in outs)
+    assert not any(o.badflag for o in outs2) and _Dev.syncs == 1
+    outs = ufunc.minmaximum(ga)
+    outs[0].badflag = False                                   # an explicit setting wins over the flag in flight
+    assert outs[0].store._pend is None and not outs[0].badflag and outs[1].badflag
+    b = bad.setnantobad(ga)
+    assert b.store._pend is not None and b.badflag
+    # the ring wraps: a slot still in flight is settled before it is handed out again
+    keep = [ufunc.minmaximum(ga) for _ in range(E.FlagRing.SLOTS + 3)]
+    assert all(o.badflag for o in keep[0]) and all(o.badflag for o in keep[-1])

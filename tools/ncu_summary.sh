@@ -5,7 +5,7 @@
 set -u
 OUT="$1"; shift
 mkdir -p "$OUT"
-K="regex:reduce_rows_kernel|ew_tile_kernel|ew_kernel|mm_dmma|mm_exact_kernel|inner_warp_kernel|minmaximum_warp_kernel|scan_chunk_kernel|axisvals_kernel|nind_kernel|mm_dmma_tma_kernel|collapse_records_kernel"
+K="regex:reduce_rows_kernel|ew_tile_kernel|ew_kernel|mm_dmma|mm_exact_kernel|inner_warp_kernel|minmaximum_warp_kernel|scan_chunk_kernel|axisvals_kernel|nind_kernel|mm_dmma_tma_kernel|collapse_records_kernel|scan_onepass_kernel"
 for op in "$@"; do
   REP=/tmp/prof_$(echo $op | tr ':' '_')
   ncu --set full --clock-control none --import-source on -k "$K" -s 1 -c 1 -f -o $REP python tools/prof_one.py $op 3 > /dev/null 2>&1

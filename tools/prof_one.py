@@ -65,6 +65,16 @@ elif op in ("setbadif", "inner", "minmaximum", "cumusumover", "sequence"):
         f = P.prepare_op("cumusumover", [wrap(x, T.F, [16384, n // 16384])], [wrap(torch.empty_like(x), T.F, [16384, n // 16384])])
     else:
         f = P.prepare_op("axisvalues", [of], [of])
+elif op in ("scan1d", "scan1d_bad", "minmax1d"):
+    n = 2 ** 28
+    x = torch.randint(-8, 9, (n,), device=dev).float()
+    px = wrap(x, T.F, [n])
+    if op == "minmax1d":
+        f = P.prepare_op("minmaximum", [px], [P.PDL.empty(T.F, [], eng), P.PDL.empty(T.F, [], eng),
+                                              P.PDL.empty(T.IND, [], eng), P.PDL.empty(T.IND, [], eng)])
+    else:
+        px.badflag = op.endswith("bad")
+        f = P.prepare_op("cumusumover", [px], [P.PDL.empty(T.F, [n], eng)])
 elif op.startswith(("ew:", "rd:")):
     # generic: ew:<op>:<type>:<good|bad> / rd:<op>:<type>:<good|bad> on 1 GiB operands (as tools/sweep.py)
     kind, name, tname, mode = op.split(":")
