@@ -12,6 +12,7 @@
 //      multiple of SC_CHUNK elements sized for one resident wave of warps: (1) chunk totals,
 //      (2) scan_chunk_prefix_kernel: exclusive scan of the totals per row, (3) the scan again with
 //      the chunk's carry-in.  3 passes of traffic instead of the ideal 2, but every SM works on the row.
+#include <cstdio>
 #include <cstring>
 #include "common.cuh"
 namespace pdlb200 {

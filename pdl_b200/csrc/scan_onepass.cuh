@@ -2,36 +2,73 @@
 // ndarray is the common case, lib/PDL/Ufunc.pd:120-141).  Ideal traffic: every element is read once and
 // written once (the three-pass chunked path reads it twice).
 //
-// One persistent CTA per SM, 23 warps with fixed roles around a ring of OP_SLOTS shared-memory tiles of 40 KB;
-// tiles move in AND out with bulk-async copies (cp.async.bulk, UBLKCP), the scan happens in place in shared memory:
-//   producer (1 thread)  takes the next tile number from a global counter (tiles are handed out in the order
-//                        CTAs actually run, so a look-back never waits on a CTA that is not resident) and
-//                        fills the slot with ONE bulk copy armed on an mbarrier (expect_tx);
-//   aggregators (4 warps) run AHEAD of the scanners: per-segment totals of the tile, the tile aggregate, and
+// One persistent CTA per SM, 19 warps with fixed roles around a ring of 6 shared-memory tiles of 36 KB; tiles move
+// in AND out with bulk-async copies (cp.async.bulk, UBLKCP), the scan happens in place in shared memory:
+//   producer (1 thread)  takes the next tile number from a global counter when a slot is free (tiles are handed out
+//                        in the order CTAs actually run, so a look-back never waits on a CTA that is not resident)
+//                        and fills the slot with ONE bulk copy armed on an mbarrier (expect_tx);
+//   aggregators (8 warps) run AHEAD of the scanners: per-segment totals of the tile, the tile aggregate, and
 //                        the tile's descriptor {status A, aggregate} published to global;
-//   prefix warp          decoupled look-back over the 32 preceding descriptors per round trip until it meets
-//                        an inclusive prefix (status P), then publishes {P, prefix+aggregate} — before the
-//                        tile itself is scanned, so successors are released early;
-//   scanners (16 warps)  one segment each; every LANE owns OP_VPL consecutive 16-byte vectors (5: an odd lane
-//                        stride of 80 bytes keeps the 128-bit shared-memory accesses bank-conflict free): a
-//                        serial in-lane scan, ONE warp shuffle scan of the lane totals per tile, results written
-//                        back in place (≈ 0.1 warp instructions per element);
+//   prefix warp          decoupled look-back over the 32 preceding descriptors per round trip (the first poll is
+//                        issued while the aggregators still work on the tile) until it meets an inclusive prefix
+//                        (status P), then {P, prefix+aggregate} published — before the tile itself is scanned,
+//                        so successors are released early;
+//   scanners (8 warps)   one segment each; every LANE owns OP_VPL consecutive 16-byte vectors (9: an odd lane
+//                        stride keeps the 128-bit shared-memory accesses bank-conflict free): a serial in-lane
+//                        scan, ONE warp shuffle scan of the lane totals per tile, results written back in place;
 //   storer (1 thread)    ONE bulk copy shared -> global per tile; the slot is free again once it has been read.
 // Descriptors are one 64-bit word {status, value} for 4-byte results and one 16-byte vector {status, value}
 // for 8-byte results; the array and the counter are cleared by one memset per launch.
+// Tuning notes (B200, stage timers below): the ring is latency-bound — a slot is held from the
+// load's issue until its prefix is known and the tile is stored — so what pays is more slots in flight and fewer
+// warps contending for issue slots (16 scanner warps x 5 slots of 40 KB: 0.82 of the copy peak; 8 x 6 x 36 KB: 0.88);
+// wider look-back windows (2..8 x 32 descriptors per poll) and several prefix warps per CTA both made it slower.
 #pragma once
 
 namespace pdlb200 {
 
-constexpr int OP_NSCAN = 16;
-constexpr int OP_NAGG = 4;
-constexpr int OP_VPL = 5;                                        // 16-byte vectors per scanner lane
-constexpr int OP_SEG_VECS = 32 * OP_VPL;                         // 160 vectors per segment
-constexpr int OP_TILE_BYTES = OP_NSCAN * OP_SEG_VECS * 16;       // 40960
-constexpr int OP_SLOTS = 5;
-constexpr int OP_THREADS = (OP_NSCAN + OP_NAGG + 3) * 32;
+#ifndef OP_NSCAN_V
+#define OP_NSCAN_V 8
+#endif
+#ifndef OP_VPL_V
+#define OP_VPL_V 9
+#endif
+#ifndef OP_SLOTS_V
+#define OP_SLOTS_V 6
+#endif
+constexpr int OP_NSCAN = OP_NSCAN_V;
+#ifndef OP_NAGG_V
+#define OP_NAGG_V 8
+#endif
+constexpr int OP_NAGG = OP_NAGG_V;
+constexpr int OP_VPL = OP_VPL_V;                                        // 16-byte vectors per scanner lane
+constexpr int OP_SEG_VECS = 32 * OP_VPL;                         // 96 vectors per segment
+constexpr int OP_TILE_BYTES = OP_NSCAN * OP_SEG_VECS * 16;       // 24576
+constexpr int OP_SLOTS = OP_SLOTS_V;
+constexpr int OP_NPREF = 1;                                      // prefix warps: look-backs in flight per SM
+constexpr int OP_THREADS = (OP_NSCAN + OP_NAGG + OP_NPREF + 2) * 32;
+
+// Stage timers for tuning (clock64 sums per CTA, 16 slots): compiled in only with -DPDLB200_SCAN_PROF
+#ifdef PDLB200_SCAN_PROF
+#define OP_PROF_DECL long long prof_acc[16] = {0}; (void)prof_acc;
+#define OP_PROF_T(v) const long long v = clock64();
+#define OP_PROF_ADD(k, v) prof_acc[k] += clock64() - v;
+#define OP_PROF_INC(k) prof_acc[k] += 1;
+#define OP_PROF_OUT(k) if (p.prof) p.prof[blockIdx.x * 16 + k] = prof_acc[k];
+#define OP_PROF_STAMP(s) c.stamp[s] = clock64();
+#define OP_PROF_SINCE(k, s) prof_acc[k] += clock64() - c.stamp[s];
+#else
+#define OP_PROF_DECL
+#define OP_PROF_T(v)
+#define OP_PROF_ADD(k, v)
+#define OP_PROF_INC(k)
+#define OP_PROF_OUT(k)
+#define OP_PROF_STAMP(s)
+#define OP_PROF_SINCE(k, s)
+#endif
 
 struct OpPlan {
+  long long *prof;
   const char *a; char *b;
   unsigned long long *desc;
   unsigned int *counter;
@@ -98,13 +135,17 @@ template <class O> struct OpDesc<O, 8> {
   }
 };
 
-template <class T, class O, bool PROD, bool BAD>
+// BADK: 0 = no BAD values, 1 = BAD by value, 2 = BAD is NaN (compile-time: one compare per element in the hot loops)
+template <class T, class O, bool PROD, int BADK>
 __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __grid_constant__ OpPlan p) {
   extern __shared__ __align__(128) unsigned char op_tiles[];
   __shared__ struct {
     O segtot[OP_SLOTS][OP_NSCAN], segpre[OP_SLOTS][OP_NSCAN];
     O tagg[OP_SLOTS], tpre[OP_SLOTS];
     int stile[OP_SLOTS];
+#ifdef PDLB200_SCAN_PROF
+    long long stamp[OP_SLOTS];
+#endif
     uint64_t full[OP_SLOTS], aggd[OP_SLOTS], pref[OP_SLOTS], scanned[OP_SLOTS], empty[OP_SLOTS];
   } c;
   constexpr int TE = OP_TILE_BYTES / (int)sizeof(T);
@@ -116,7 +157,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
   // broadcast from lane 0: tells the compiler the role (and every tile number below) is warp-uniform, so the
   // shuffles in the role loops need no reconvergence bookkeeping
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const bool badnan = p.abadnan != 0;
+  constexpr bool BAD = BADK != 0, badnan = BADK == 2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < OP_SLOTS; s++) {
@@ -127,55 +168,88 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
   }
   __syncthreads();
 
-  if (wid == OP_NSCAN + OP_NAGG + 1) {
+  if (wid == OP_NSCAN + OP_NAGG + OP_NPREF) {
     // ---- producer ----
     if (lane != 0) return;
-    // the tile number is fetched one tile ahead, so the atomic's round trip is not in series with the slot wait
-    long long t = (long long)atomicAdd(p.counter, 1u);
+    OP_PROF_DECL
     for (unsigned it = 0;; it++) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
+      OP_PROF_T(a0)
       if (it >= OP_SLOTS) op_mbar_wait(&c.empty[s], (u - 1) & 1);
-      if (t >= p.ntiles) { c.stile[s] = -1; op_mbar_arrive(&c.full[s]); return; }
+      OP_PROF_ADD(0, a0)
+      // taken only when the slot is free: a tile claimed early but loaded late would stall every successor's look-back
+      OP_PROF_T(a1)
+      const long long t = (long long)atomicAdd(p.counter, 1u);
+      OP_PROF_ADD(1, a1)
+      if (t >= p.ntiles) {
+        // end of work, posted for OP_NPREF consecutive iterations: every prefix warp meets it in its own sequence
+        c.stile[s] = -1; op_mbar_arrive(&c.full[s]);
+        for (unsigned e = 1; e < OP_NPREF; e++) {
+          const unsigned it2 = it + e;
+          const int s2 = it2 % OP_SLOTS;
+          if (it2 >= OP_SLOTS) op_mbar_wait(&c.empty[s2], (it2 / OP_SLOTS - 1) & 1);
+          c.stile[s2] = -1; op_mbar_arrive(&c.full[s2]);
+        }
+        OP_PROF_OUT(0) OP_PROF_OUT(1)
+        return;
+      }
       c.stile[s] = (int)t;
+      OP_PROF_STAMP(s)
       const int64_t row = t / p.tpr, j = t - row * p.tpr;
       const int64_t left = p.n - j * TE;
       const unsigned bytes = (unsigned)((left < TE ? left : TE) * (int64_t)sizeof(T));
       op_mbar_expect_tx(&c.full[s], bytes);
       op_bulk_load(op_tiles + (size_t)s * OP_TILE_BYTES, p.a + (row * p.sa + j * TE) * (int64_t)sizeof(T), bytes, &c.full[s]);
-      t = (long long)atomicAdd(p.counter, 1u);
     }
   }
 
-  if (wid == OP_NSCAN + OP_NAGG + 2) {
+  if (wid == OP_NSCAN + OP_NAGG + OP_NPREF + 1) {
     // ---- storer ----
     if (lane != 0) return;
+    OP_PROF_DECL
     for (unsigned it = 0;; it++) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
+      OP_PROF_T(a9)
       op_mbar_wait(&c.scanned[s], u & 1);
+      OP_PROF_ADD(9, a9)
       const long long t = c.stile[s];
       if (t < 0) break;
+      OP_PROF_T(a10)
       const int64_t row = t / p.tpr, j = t - row * p.tpr;
       const int64_t left = p.n - j * TE;
       const unsigned bytes = (unsigned)((left < TE ? left : TE) * (int64_t)sizeof(O));
       op_bulk_store(p.b + (row * p.sb + j * TE) * (int64_t)sizeof(O), op_tiles + (size_t)s * OP_TILE_BYTES, bytes);
       asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");     // the slot has been read: reusable
+      OP_PROF_ADD(10, a10)
       op_mbar_arrive(&c.empty[s]);
     }
     asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    OP_PROF_OUT(9) OP_PROF_OUT(10)
     return;
   }
 
   if (wid >= OP_NSCAN && wid < OP_NSCAN + OP_NAGG) {
     // ---- aggregators: OP_NSCAN / OP_NAGG segments per warp ----
     const int aw = wid - OP_NSCAN;
+    int nend = 0;
+    OP_PROF_DECL
     for (unsigned it = 0;; it++) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
+      OP_PROF_T(a11)
       op_mbar_wait(&c.full[s], u & 1);
+      OP_PROF_ADD(11, a11)
       const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
-      if (t < 0) { if (aw == 0 && lane == 0) op_mbar_arrive(&c.aggd[s]); return; }
+      if (t < 0) {
+        if (aw == 0 && lane == 0) op_mbar_arrive(&c.aggd[s]);
+        if (++nend < OP_NPREF) continue;
+        if (aw == 0 && lane == 0) { OP_PROF_OUT(11) OP_PROF_OUT(2) OP_PROF_OUT(3) }
+        return;
+      }
+      OP_PROF_SINCE(2, s)
+      OP_PROF_T(a3)
       const int64_t j = t % p.tpr;
       const int64_t left = p.n - j * TE;
       const int nvec = (int)((left < TE ? left : TE) / VEC);
@@ -210,41 +284,51 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
         c.tagg[s] = agg;
         OpDesc<O>::put(p.desc, t, j == 0 ? 2u : 1u, agg);
         op_mbar_arrive(&c.aggd[s]);
+        OP_PROF_ADD(3, a3)
       }
     }
   }
 
-  if (wid == OP_NSCAN + OP_NAGG) {
-    // ---- prefix warp: decoupled look-back ----
-    for (unsigned it = 0;; it++) {
+  if (wid >= OP_NSCAN + OP_NAGG && wid < OP_NSCAN + OP_NAGG + OP_NPREF) {
+    // ---- prefix warps: decoupled look-back, warp k takes every OP_NPREF-th tile of this CTA ----
+    OP_PROF_DECL
+    for (unsigned it = wid - (OP_NSCAN + OP_NAGG);; it += OP_NPREF) {
       const int s = it % OP_SLOTS;
       const unsigned u = it / OP_SLOTS;
-      op_mbar_wait(&c.aggd[s], u & 1);
+      // the tile number is known once the tile has landed: poll the 32 predecessors NOW, while the aggregators
+      // are still working on the tile — one L2 round trip (≈ 1000 cycles under load) off the serial path
+      op_mbar_wait(&c.full[s], u & 1);
       const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
-      if (t < 0) { if (lane == 0) op_mbar_arrive(&c.pref[s]); return; }
-      const int64_t j = t % p.tpr;
+      int64_t j = 0, lowest = 0, pos = 0;
+      unsigned st = 1; O v = ident;
+      if (t >= 0) {
+        j = t % p.tpr; lowest = t - j; pos = (int64_t)t - 1;       // tile `lowest` starts the row: always published as P
+        if (j > 0 && pos - lane >= lowest) st = OpDesc<O>::get(p.desc, pos - lane, v);
+      }
+      OP_PROF_T(a12)
+      op_mbar_wait(&c.aggd[s], u & 1);
+      OP_PROF_ADD(12, a12)
+      if (t < 0) { if (lane == 0) { op_mbar_arrive(&c.pref[s]); if (wid == OP_NSCAN + OP_NAGG) { OP_PROF_OUT(12) OP_PROF_OUT(4) OP_PROF_OUT(5) OP_PROF_OUT(6) } } return; }
+      OP_PROF_T(a4)
       O excl = ident;
       if (j > 0) {
-        const int64_t lowest = t - j;             // first tile of this row: always published as P
-        int64_t pos = (int64_t)t - 1;
         long long t0 = 0; bool timing = false;
-        for (;;) {
-          const int64_t idx = pos - lane;
-          const bool valid = idx >= lowest;
-          unsigned st = 1; O v = ident;
-          if (valid) st = OpDesc<O>::get(p.desc, idx, v);
-          const unsigned pm = __ballot_sync(0xffffffffu, valid && st == 2);
-          const unsigned zm = __ballot_sync(0xffffffffu, valid && st == 0);
+        for (bool first = true;; first = false) {
+          if (!first) { st = 1; v = ident; if (pos - lane >= lowest) st = OpDesc<O>::get(p.desc, pos - lane, v); }
+          const unsigned pm = __ballot_sync(0xffffffffu, st == 2);
+          const unsigned zm = __ballot_sync(0xffffffffu, st == 0);
           const int np = pm ? __ffs(pm) - 1 : 32;
           const unsigned need = np < 31 ? ((2u << np) - 1u) : 0xffffffffu;
+          OP_PROF_INC(5)
           if (zm & need) {
+            OP_PROF_INC(6)
             // a predecessor has not published yet: it is resident (tiles are taken in execution order)
             if (!timing) { timing = true; t0 = clock64(); }
             else if (clock64() - t0 > 20000000000ll) __trap();     // ≈10 s: fail loudly instead of hanging the GPU
             __nanosleep(20);
             continue;
           }
-          O x = (valid && lane <= np) ? v : ident;
+          O x = lane <= np ? v : ident;
 #pragma unroll
           for (int d = 16; d >= 1; d >>= 1) x = scan_op<O, PROD>(x, shfl_xor_t(x, d));
           excl = scan_op<O, PROD>(x, excl);
@@ -257,18 +341,23 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
         if (j > 0) OpDesc<O>::put(p.desc, t, 2u, scan_op<O, PROD>(excl, c.tagg[s]));
         op_mbar_arrive(&c.pref[s]);
       }
+      OP_PROF_ADD(4, a4)
       __syncwarp();
     }
   }
 
   // ---- scanners: warp `wid` owns segment `wid` of every tile, lane owns OP_VPL consecutive vectors of it ----
+  OP_PROF_DECL
   for (unsigned it = 0;; it++) {
     const int s = it % OP_SLOTS;
     const unsigned u = it / OP_SLOTS;
+    OP_PROF_T(a7)
     op_mbar_wait(&c.pref[s], u & 1);
     op_mbar_wait(&c.full[s], u & 1);                // already complete: makes the bulk copy's writes visible to this warp
+    OP_PROF_ADD(7, a7)
     const int t = __shfl_sync(0xffffffffu, c.stile[s], 0);
-    if (t < 0) { if (lane == 0) op_mbar_arrive(&c.scanned[s]); return; }
+    if (t < 0) { if (lane == 0) { op_mbar_arrive(&c.scanned[s]); if (wid == 0) { OP_PROF_OUT(7) OP_PROF_OUT(8) } } return; }
+    OP_PROF_T(a8)
     const int64_t j = t % p.tpr;
     const int64_t left = p.n - j * TE;
     const int nvec = (int)((left < TE ? left : TE) / VEC);
@@ -280,7 +369,8 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
 #pragma unroll
       for (int k = 0; k < OP_VPL; k++) if (v0 + k < nvec) in[k].q = tv[v0 + k];
       O x[OP_VPL][VEC];
-      unsigned bdm = 0;
+      using Mask = typename std::conditional<(OP_VPL * VEC > 32), unsigned long long, unsigned>::type;
+      Mask bdm = 0;
       O run = ident;
 #pragma unroll
       for (int k = 0; k < OP_VPL; k++) {
@@ -289,7 +379,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
         for (int e = 0; e < VEC; e++) {
           const T val = inr ? in[k].e[e] : T(0);
           const bool bd = BAD && inr && is_bad(val, abad, badnan);
-          if (BAD && bd) bdm |= 1u << (k * VEC + e);
+          if (BAD && bd) bdm |= Mask(1) << (k * VEC + e);
           if (inr && !bd) run = scan_op<O, PROD>(run, (O)val);
           x[k][e] = run;
         }
@@ -309,13 +399,14 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
           Pack<O> out;
 #pragma unroll
           for (int e = 0; e < VEC; e++)
-            out.e[e] = (BAD && ((bdm >> (k * VEC + e)) & 1u)) ? bbad : scan_op<O, PROD>(base, x[k][e]);
+            out.e[e] = (BAD && ((bdm >> (k * VEC + e)) & Mask(1))) ? bbad : scan_op<O, PROD>(base, x[k][e]);
           tv[v0 + k] = out.q;
         }
       }
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the bulk store
     }
     __syncwarp();
+    OP_PROF_ADD(8, a8)
     if (lane == 0) op_mbar_arrive(&c.scanned[s]);
   }
 }
@@ -350,16 +441,47 @@ static bool scan_onepass_try(const ScPlan &p, cudaStream_t s, const char *name, 
     q.counter = (unsigned int *)(scr + dbytes);
     if (cudaMemsetAsync(scr, 0, dbytes + 16, s) != cudaSuccess) { *rc = E.fail(PDLB200_ECUDA, "%s: memset failed", name); return true; }
     static const bool attr = [] {
-      return cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  OP_SLOTS * OP_TILE_BYTES) == cudaSuccess &&
-             cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  OP_SLOTS * OP_TILE_BYTES) == cudaSuccess;
+      bool ok = cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     OP_SLOTS * OP_TILE_BYTES) == cudaSuccess &&
+                cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     OP_SLOTS * OP_TILE_BYTES) == cudaSuccess;
+      if constexpr (!tt<T>::is_int)
+        ok = ok && cudaFuncSetAttribute(scan_onepass_kernel<T, O, PROD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        OP_SLOTS * OP_TILE_BYTES) == cudaSuccess;
+      return ok;
     }();
     if (!attr) { cudaGetLastError(); return false; }
     const int64_t g = ntiles < sm_count() ? ntiles : sm_count();
-    if (q.badmode) scan_onepass_kernel<T, O, PROD, true><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
-    else scan_onepass_kernel<T, O, PROD, false><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
+#ifdef PDLB200_SCAN_PROF
+    static long long *prof_dev = nullptr;
+    if (!prof_dev) cudaMalloc(&prof_dev, 16 * 8 * 1024);
+    cudaMemsetAsync(prof_dev, 0, 16 * 8 * 1024, s);
+    q.prof = prof_dev;
+#endif
+    bool launched = false;
+    if constexpr (!tt<T>::is_int) {
+      if (q.badmode && q.abadnan) { scan_onepass_kernel<T, O, PROD, 2><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q); launched = true; }
+    }
+    if (!launched) {
+      if (q.badmode) scan_onepass_kernel<T, O, PROD, 1><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
+      else scan_onepass_kernel<T, O, PROD, 0><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
+    }
     note_launch(name);
+#ifdef PDLB200_SCAN_PROF
+    if (getenv("PDLB200_SCAN_PROF_PRINT")) {
+      static long long host[16 * 1024];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(host, prof_dev, sizeof host, cudaMemcpyDeviceToHost);
+      double sum[16] = {0};
+      for (int64_t b = 0; b < g; b++) for (int k = 0; k < 16; k++) sum[k] += (double)host[b * 16 + k];
+      const double tiles_per_cta = (double)ntiles / (double)g;
+      fprintf(stderr, "scan_prof tiles/cta %.1f | per tile (cycles): empty_wait %.0f atomic %.0f load_lat %.0f agg %.0f "
+              "lookback %.0f (rounds %.2f stalled %.2f) scan_wait %.0f scan %.0f store_wait %.0f store %.0f agg_wait_full %.0f prefix_wait_agg %.0f\n",
+              tiles_per_cta, sum[0] / g / tiles_per_cta, sum[1] / g / tiles_per_cta, sum[2] / g / tiles_per_cta, sum[3] / g / tiles_per_cta,
+              sum[4] * OP_NPREF / g / tiles_per_cta, sum[5] * OP_NPREF / g / tiles_per_cta, sum[6] * OP_NPREF / g / tiles_per_cta, sum[7] / g / tiles_per_cta,
+              sum[8] / g / tiles_per_cta, sum[9] / g / tiles_per_cta, sum[10] / g / tiles_per_cta, sum[11] / g / tiles_per_cta, sum[12] * OP_NPREF / g / tiles_per_cta);
+    }
+#endif
     cudaError_t e = cudaGetLastError();
     *rc = e == cudaSuccess ? PDLB200_OK : E.fail(PDLB200_ECUDA, "%s: %s", name, cudaGetErrorString(e));
     return true;

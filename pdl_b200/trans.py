@@ -291,6 +291,9 @@ def _readdata_flagged(engine, tr, name):
     a 1-tuple when the engine defers the read-back (no stream synchronise inside the call)."""
     ring = getattr(engine, "flag_ring", None) if name in _FLAG_DEFERRABLE else None
     if ring is None:
+        if tr.tflags:                                  # a cached descriptor last used by a deferring engine
+            import ctypes as _C
+            tr.anybad, tr.tflags = _C.pointer(tr._anybad), 0
         engine.readdata(tr)
         return int(tr._anybad.value)
     slot, ptr = ring.take()

@@ -178,7 +178,7 @@ def main():
         px.badflag = False
         o0 = P.PDL.empty(T.F, [], eng)
         row("next inner of two float[2^28] (dot product)", lambda: P.run_op("inner", [px, py_], [o0]), 8 * n)
-        row("next cumusumover float[2^28] (one row, 3-pass chunked scan)", lambda: P.run_op("cumusumover", [py_], [of]), 8 * n)
+        row("next cumusumover float[2^28] (one row, single-pass look-back scan)", lambda: P.run_op("cumusumover", [py_], [of]), 8 * n)
         mm = [P.PDL.empty(T.F, [], eng), P.PDL.empty(T.F, [], eng), P.PDL.empty(T.IND, [], eng), P.PDL.empty(T.IND, [], eng)]
         # minmaximum ends in a flag read-back + stream sync (float rows may be all-NaN), so host-side descriptor
         # preparation is not hidden behind the kernel: time the prepared descriptor (one C-ABI call)
