@@ -161,6 +161,175 @@ mm_dmma_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   }
 }
 
+// ===== stream-K version: persistent CTAs, the (tile, k-tile) iteration space cut evenly across them =====
+// A grid of 128x128 tiles only fills the machine in whole waves: 2048^3 is 256 tiles on 148 SMs = 1.73 waves that take
+// the time of 2.  Here G <= #SMs persistent CTAs each take a CONTIGUOUS range of the global iteration space
+// (iteration = one k-tile of one output tile, tiles in row-major order), so every SM does the same amount of DMMA
+// work and the TMA ring never drains between tiles.  A tile whose k range is cut is finished by the CTA that holds its
+// k = 0 end: that CTA reaches the tile LAST in its own range, whereas the CTAs holding the rest of the tile reach it
+// FIRST — they have written their partial accumulators (thread-linear layout, 128 KB per CTA, L2-resident) and
+// raised their flag long before the finisher asks; all CTAs are resident (one per SM), so the wait cannot deadlock.
+// The partial sums are added in k order: the result does not depend on timing.
+struct SkPlan {
+  double *ws;          // [G][32][512] partial accumulators
+  int *flags;          // [G], zeroed per launch
+  int KT, ntx, nty, G;
+  long long total;     // ntx * nty * KT iterations
+};
+
+__device__ __forceinline__ void sk_range(const SkPlan &k, int b, long long &lo, long long &hi) {
+  lo = k.total * b / k.G; hi = k.total * (b + 1) / k.G;
+}
+
+__global__ void __launch_bounds__(TM_THREADS, 1)
+mm_dmma_tma_sk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ MmPlan p,
+                      const __grid_constant__ SkPlan k) {
+  extern __shared__ unsigned char tm_smem_raw[];
+  unsigned char *smem = tm_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(tm_smem_raw) & 1023u)) & 1023u);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)TM_STAGES * TM_STAGE_BYTES);
+  uint64_t *empty = full + TM_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long lo, hi;
+  sk_range(k, blockIdx.x, lo, hi);
+  const int nloc = (int)(hi - lo);                       // iterations of this CTA
+
+  if (tid == 0) {
+    for (int s = 0; s < TM_STAGES; s++) { tm_mbar_init(&full[s], 1); tm_mbar_init(&empty[s], TM_NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" :: "l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" :: "l"(&mapB) : "memory");
+  }
+  __syncthreads();
+  // iterations are issued in order: the coordinates of the NEXT one are kept incrementally (no divisions on the
+  // issuing lane's path — it is also a consumer, and the slowest warp paces the ring)
+  int p_k, p_h, p_w;
+  {
+    const int tile = (int)(lo / k.KT);
+    p_k = (int)(lo - (long long)tile * k.KT) * TM_BK;
+    p_h = (tile / k.ntx) * TM_BM; p_w = (tile % k.ntx) * TM_BN;
+  }
+  const int k_end = k.KT * TM_BK, w_end = k.ntx * TM_BN;
+  auto issue = [&](int q) {
+    const int s = q % TM_STAGES;
+    unsigned char *dA = smem + (size_t)s * TM_STAGE_BYTES, *dB = dA + TM_A_BYTES;
+    tm_mbar_expect_tx(&full[s], TM_STAGE_BYTES);
+    tm_load_2d(dA, &mapA, p_k, p_h, &full[s]);
+#pragma unroll
+    for (int b = 0; b < 8; b++) tm_load_2d(dB + b * 2048, &mapB, p_w + 16 * b, p_k, &full[s]);
+    p_k += TM_BK;
+    if (p_k >= k_end) { p_k = 0; p_w += TM_BN; if (p_w >= w_end) { p_w = 0; p_h += TM_BM; } }
+  };
+  if (tid == 0)
+    for (int q = 0; q < TM_STAGES && q < nloc; q++) issue(q);
+
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int prow = ((g & 2) << 1) | (g & 1) | ((g & 4) >> 1);
+  unsigned aoff[4], boff[4][2];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int kk = 8 * (s >> 1) + ((s & 1) ? ((t4 == 0) ? 1 : (t4 == 1) ? 2 : (t4 == 2) ? 5 : 6)
+                                           : ((t4 == 0) ? 0 : (t4 == 1) ? 3 : (t4 == 2) ? 4 : 7));
+    aoff[s] = (unsigned)(prow * 128 + ((((kk >> 1) ^ prow) & 7) << 4) + ((kk & 1) << 3));
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++)
+      boff[s][jj] = (unsigned)(kk * 128 + ((((jj * 4 + (g >> 1)) ^ kk) & 7) << 4) + ((g & 1) << 3));
+  }
+  double *C = reinterpret_cast<double *>(p.c);
+  const bool c_vec = (p.icw == 1) && ((((uintptr_t)C) & 15) == 0) && ((p.ich & 1) == 0);
+
+  int q = 0;
+  while (q < nloc) {
+    const long long g0 = lo + q;
+    const int tile = (int)(g0 / k.KT), kt0 = (int)(g0 - (long long)tile * k.KT);
+    const int nk = (k.KT - kt0 < nloc - q) ? k.KT - kt0 : nloc - q;    // k-tiles of this segment
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    for (int it = 0; it < nk; it++, q++) {
+      const int s = q % TM_STAGES;
+      if (tid == 0 && q >= 1) {
+        const int nq = q - 1 + TM_STAGES;                // refill the slot iteration q-1 used
+        if (nq < nloc) {
+          tm_mbar_wait(&empty[nq % TM_STAGES], ((nq / TM_STAGES) - 1) & 1);
+          issue(nq);
+        }
+      }
+      __syncwarp();
+      tm_mbar_wait(&full[s], (q / TM_STAGES) & 1);
+      const unsigned char *tA = smem + (size_t)s * TM_STAGE_BYTES + (wm * 32) * 128;
+      const unsigned char *tB = smem + (size_t)s * TM_STAGE_BYTES + TM_A_BYTES + (wn * 2) * 2048;
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = *reinterpret_cast<const double *>(tA + i * 1024 + aoff[ks]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) bf[j] = *reinterpret_cast<const double *>(tB + (j >> 1) * 2048 + boff[ks][j & 1]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) tm_dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      __syncwarp();
+      if (lane == 0) tm_mbar_arrive(&empty[s]);
+    }
+
+    if (kt0 != 0) {
+      // the later part of a tile that another CTA finishes: publish the partial accumulators
+      double *w = k.ws + (size_t)blockIdx.x * (32 * TM_THREADS) + tid;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { w[((i * 4 + j) * 2) * TM_THREADS] = acc[i][j][0]; w[((i * 4 + j) * 2 + 1) * TM_THREADS] = acc[i][j][1]; }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;\n" :: "l"(k.flags + blockIdx.x), "r"(1) : "memory");
+      continue;
+    }
+    if (kt0 + nk < k.KT) {
+      // this CTA holds the k = 0 end of a cut tile: add the parts of the CTAs after it, in k order
+      int done = nk;
+      for (int peer = blockIdx.x + 1; done < k.KT; peer++) {
+        long long plo, phi;
+        sk_range(k, peer, plo, phi);
+        const long long tile_end = (long long)(tile + 1) * k.KT;
+        done += (int)((phi < tile_end ? phi : tile_end) - plo);
+        if (tid == 0) {
+          int v;
+          do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(k.flags + peer) : "memory"); } while (v == 0);
+        }
+        __syncthreads();
+        const double *w = k.ws + (size_t)peer * (32 * TM_THREADS) + tid;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            acc[i][j][0] += __ldcg(w + ((i * 4 + j) * 2) * TM_THREADS);
+            acc[i][j][1] += __ldcg(w + ((i * 4 + j) * 2 + 1) * TM_THREADS);
+          }
+      }
+    }
+    const int by = tile / k.ntx, bx = tile - by * k.ntx;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int64_t h = (int64_t)by * TM_BM + wm * 32 + i * 8 + prow;
+      if (h >= p.H) continue;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int64_t w = (int64_t)bx * TM_BN + wn * 32 + j * 8 + t4 * 2;
+        if (w >= p.W) continue;
+        double *dst = C + h * p.ich + w * p.icw;
+        if (c_vec && w + 1 < p.W) *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+        else { dst[0] = acc[i][j][0]; if (w + 1 < p.W) dst[p.icw] = acc[i][j][1]; }
+      }
+    }
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
 typedef CUresult (*tm_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -208,7 +377,38 @@ int launch_matmult_tma(const pdlb200_trans *t, const MmPlan &p, const Err &E) {
     attr_set = true;
   }
   dim3 grid((unsigned)((p.W + TM_BN - 1) / TM_BN), (unsigned)((p.H + TM_BM - 1) / TM_BM), 1);
-  mm_dmma_tma_kernel<<<grid, TM_THREADS, TM_SMEM, (cudaStream_t)t->stream>>>(mapA, mapB, p);
+  cudaStream_t st = (cudaStream_t)t->stream;
+  // stream-K unless the tile grid already fills whole waves (or PDLB200_MM_STREAMK=0)
+  static const int sk_env = [] { const char *e = getenv("PDLB200_MM_STREAMK"); return e ? atoi(e) : -1; }();
+  const long long ntiles = (long long)grid.x * grid.y;
+  const int KT = (int)((p.T + TM_BK - 1) / TM_BK);
+  const long long total = ntiles * KT;
+  const int sms = sm_count();
+  const long long waves = (ntiles + sms - 1) / sms;
+  const bool uneven = ntiles * 100 < waves * sms * 97;            // the last wave leaves > 3% of the machine idle
+  if (sk_env != 0 && (uneven || sk_env == 1) && total < (1ll << 31) && ntiles < (1ll << 24)) {
+    SkPlan k;
+    long long G = total / 8;                                      // at least 8 k-tiles (k depth 128) per CTA
+    if (G > sms) G = sms;
+    if (G < 1) G = 1;
+    k.G = (int)G; k.KT = KT; k.ntx = (int)grid.x; k.nty = (int)grid.y; k.total = total;
+    const size_t wsb = (size_t)G * 32 * TM_THREADS * sizeof(double);
+    char *scr = (char *)scratch(wsb + (size_t)G * sizeof(int), st);
+    if (scr) {
+      k.ws = (double *)scr; k.flags = (int *)(scr + wsb);
+      PDLB200_CUDA_OK(cudaMemsetAsync(k.flags, 0, (size_t)G * sizeof(int), st), E);
+      static bool sk_attr = false;
+      if (!sk_attr) {
+        PDLB200_CUDA_OK(cudaFuncSetAttribute(mm_dmma_tma_sk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM), E);
+        sk_attr = true;
+      }
+      mm_dmma_tma_sk_kernel<<<(unsigned)G, TM_THREADS, TM_SMEM, st>>>(mapA, mapB, p, k);
+      note_launch("matmult_dmma_tma");
+      PDLB200_CUDA_OK(cudaGetLastError(), E);
+      return PDLB200_OK;
+    }
+  }
+  mm_dmma_tma_kernel<<<grid, TM_THREADS, TM_SMEM, st>>>(mapA, mapB, p);
   note_launch("matmult_dmma_tma");
   PDLB200_CUDA_OK(cudaGetLastError(), E);
   return PDLB200_OK;

@@ -250,10 +250,13 @@ def test_matmult_default_path_double(engines):
     assert np.all(np.abs(g - wnt) <= bound)
 
 
-@pytest.mark.parametrize("shape", [(128, 16, 128), (384, 1000, 256), (130, 17, 129), (257, 50, 131), (1024, 8, 1024), (128, 1, 128)],
+@pytest.mark.parametrize("shape", [(128, 16, 128), (384, 1000, 256), (130, 17, 129), (257, 50, 131), (1024, 8, 1024), (128, 1, 128),
+                                   (640, 2048, 384), (1300, 330, 1290)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_matmult_tma_tiles_edges_and_views(engines, shape):
-    """The TMA-staged DMMA kernel (matmult_tma.cu): full tiles, ragged edges in every dim (the hardware zero-fills
+    """The TMA-staged DMMA kernels (matmult_tma.cu; the stream-K persistent one whenever the tile grid does not fill
+    whole waves — every shape here: tiles cut across up to ~10 CTAs, partial accumulators added in k order): full
+    tiles, ragged edges in every dim (the hardware zero-fills
     the out-of-range part of a box), and operands that are windows into bigger ndarrays (row pitch != row length).
     Exactly representable inputs -> bit-exact whatever the k order inside a k-tile."""
     cuda = engines[0]
@@ -278,6 +281,13 @@ def test_matmult_tma_tiles_edges_and_views(engines, shape):
         pa, pb = P.PDL.from_numpy(abig, T.D, e), P.PDL.from_numpy(bbig, T.D, e)
         res.append(P.matmult(pa.slice(f"1:{tt},1:{h}"), pb.slice(f"3:{w + 2},1:{tt}")))
     assert_same(f"matmult-unaligned-{shape}", res[0], res[1])
+    # inexact inputs: within the summation-order bound of the reference, identical bits from run to run (the order in
+    # which the stream-K parts are added does not depend on timing), and the same bits as the one-CTA-per-tile kernel
+    a, b = rng.uniform(-1, 1, size=(h, tt)), rng.uniform(-1, 1, size=(tt, w))
+    ga, gb = P.PDL.from_numpy(a, T.D, cuda), P.PDL.from_numpy(b, T.D, cuda)
+    r1, r2 = P.matmult(ga, gb).to_numpy(), P.matmult(ga, gb).to_numpy()
+    assert np.array_equal(r1, r2)
+    assert np.all(np.abs(r1 - a @ b) <= 2 * max(tt, 2) * np.finfo(np.float64).eps * (np.abs(a) @ np.abs(b)) + 1e-300)
 
 
 @pytest.mark.parametrize("t", [T.SB, T.B, T.S, T.US], ids=lambda t: T.NAMES[t])
