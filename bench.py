@@ -516,6 +516,7 @@ def main_ours(args):
         for name, fn in (("cfg1", lambda: config_legs.cfg1(eng, device, peak)),
                          ("cfg3", lambda: config_legs.cfg3(eng, device, peak)),
                          ("cfg4", lambda: config_legs.cfg4(eng, device)),
+                         ("next_rows", lambda: config_legs.next_rows(eng, device, peak)),
                          ("perl", run_perl_bench)):
             try:
                 extra[name] = fn()

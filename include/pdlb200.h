@@ -131,9 +131,10 @@ enum {
 #define PDLB200_MAXPDLS 5   /* parameters per transformation on this path (minmaximum has 5) */
 
 /* pdlb200_trans.tflags */
-#define PDLB200_TRANS_DEFER_ANYBAD 1 /* `anybad` points to PINNED host memory (pdlb200_host_alloc): the call only
-                                      * enqueues the 4-byte copy of the flag and does NOT synchronise the stream; the
-                                      * int32 is valid once the stream has been synchronised past this call */
+#define PDLB200_TRANS_DEFER_ANYBAD 1 /* `anybad` points to PINNED, device-mapped host memory (pdlb200_host_alloc): the
+                                      * call does NOT synchronise the stream — the flag arrives by a 4-byte async copy
+                                      * or by a store from the kernel itself; the int32 is valid once the stream has
+                                      * been synchronised past this call */
 
 /* pdlb200_par.flags */
 #define PDLB200_PAR_BADFLAG 1  /* pdl->state & PDL_BADVAL                  pdl.h.PL:560-561 */
@@ -223,6 +224,9 @@ PDLB200_API void   pdlb200_dev_trim(void);            /* hand the cached blocks 
 
 /* --- plumbing ------------------------------------------------------------- */
 PDLB200_API int    pdlb200_abi_version(void);
+/* Identity of the sources this library was built from (pdl_b200/build.py source_id): the Python loader refuses a
+ * library whose id does not match the sources next to it. */
+PDLB200_API const char *pdlb200_build_id(void);
 PDLB200_API int    pdlb200_device_count(void);                 /* 0 when no usable GPU */
 PDLB200_API int    pdlb200_set_device(int dev, char *err, size_t errlen);
 PDLB200_API int    pdlb200_sm_count(void);

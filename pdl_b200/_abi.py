@@ -6,6 +6,7 @@ maintainer of the reference would write in XS, in ctypes.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 MAXDIMS = 16
@@ -76,7 +77,7 @@ SYMBOLS = [
     "pdlb200_readdata", "pdlb200_elementwise", "pdlb200_reduce", "pdlb200_matmult",
     "pdlb200_buf_new", "pdlb200_buf_free", "pdlb200_buf_nbytes", "pdlb200_buf_devptr",
     "pdlb200_buf_upload", "pdlb200_buf_download", "pdlb200_buf_device_dirty",
-    "pdlb200_abi_version", "pdlb200_device_count", "pdlb200_set_device", "pdlb200_sm_count",
+    "pdlb200_abi_version", "pdlb200_build_id", "pdlb200_device_count", "pdlb200_set_device", "pdlb200_sm_count",
     "pdlb200_sync", "pdlb200_host_alloc", "pdlb200_host_free", "pdlb200_memcpy_h2d",
     "pdlb200_memcpy_d2h", "pdlb200_managed_alloc", "pdlb200_managed_free", "pdlb200_managed_trim", "pdlb200_ptr_kind",
     "pdlb200_prefetch", "pdlb200_launch_count", "pdlb200_last_kernel", "pdlb200_op_name",
@@ -109,6 +110,18 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -m pdl_b200.build` "
             "(pdl_b200 has no CPU fallback)")
     lib = C.CDLL(str(LIB_PATH))
+    # a prebuilt library must match the sources it ships with (it travels to the GPU box as a file): refuse a stale one
+    try:
+        from .build import source_id, CSRC
+        want = source_id() if CSRC.is_dir() else None
+    except Exception:  # a source-less install: nothing to compare against
+        want = None
+    if want is not None and os.environ.get("PDLB200_SKIP_BUILD_ID") != "1":
+        lib.pdlb200_build_id.restype = C.c_char_p
+        have = (lib.pdlb200_build_id() or b"").decode()
+        if have != want:
+            raise LibraryMissing(f"{LIB_PATH} was built from other sources (library {have}, sources {want}): "
+                                 "rebuild it with `python -m pdl_b200.build`")
     errargs = [C.c_char_p, C.c_size_t]
     for name in ("pdlb200_readdata", "pdlb200_elementwise", "pdlb200_reduce", "pdlb200_matmult"):
         f = getattr(lib, name)
@@ -129,6 +142,7 @@ def load():
     lib.pdlb200_buf_device_dirty.argtypes = [C.c_void_p]
     lib.pdlb200_buf_device_dirty.restype = C.c_int
     lib.pdlb200_abi_version.restype = C.c_int
+    lib.pdlb200_build_id.restype = C.c_char_p
     lib.pdlb200_device_count.restype = C.c_int
     lib.pdlb200_set_device.argtypes = [C.c_int] + errargs
     lib.pdlb200_set_device.restype = C.c_int

@@ -32,6 +32,20 @@ FLAGS = [
 ]
 
 
+def source_id() -> str:
+    """Identity of what the library is built FROM: sha256 over every file under csrc/, include/pdlb200.h and the
+    compiler flags.  It is compiled into the library (pdlb200_build_id) and compared at load time, so a prebuilt
+    .so that no longer matches the sources next to it (an mtime-preserving copy, a forgotten rebuild) is refused
+    instead of silently tested."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "pdlb200.h"]
+    for f in files:
+        h.update(f.name.encode() + b"\0" + f.read_bytes() + b"\0")
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def _stale(target: Path, deps) -> bool:
     if not target.exists():
         return True
@@ -56,15 +70,19 @@ def _deps(src: Path, seen=None) -> set:
 def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
+    sid = source_id()
+    stamp = OBJ / "api.buildid"                      # api.cu carries the id: recompile it whenever the id moves
     todo = []
     for src in sources:
         obj = OBJ / (src.stem + ".o")
-        if force or _stale(obj, [src, *_deps(src)]):
+        if force or _stale(obj, [src, *_deps(src)]) or (src.stem == "api" and (not stamp.exists() or stamp.read_text() != sid)):
             todo.append((src, obj))
 
     def compile_one(pair):
         src, obj = pair
         cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        if src.stem == "api":
+            cmd.insert(1, f'-DPDLB200_BUILD_ID="{sid}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -78,6 +96,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
                     raise RuntimeError(f"nvcc failed on {src.name}")
                 if verbose or r.stderr.strip():
                     sys.stderr.write(f"--- {src.name}\n{r.stderr}")
+    stamp.write_text(sid)
     objs = [OBJ / (s.stem + ".o") for s in sources]
     if force or todo or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),

@@ -157,6 +157,10 @@ using namespace pdlb200;
 extern "C" {
 
 int pdlb200_abi_version(void) { return PDLB200_ABI_VERSION; }
+#ifndef PDLB200_BUILD_ID
+#define PDLB200_BUILD_ID "unknown"
+#endif
+const char *pdlb200_build_id(void) { return PDLB200_BUILD_ID; }
 int pdlb200_device_count(void) { return probe_devices(); }
 int pdlb200_sm_count(void) { return probe_devices() > 0 ? sm_count() : 0; }
 uint64_t pdlb200_launch_count(void) { return g_launches.load(); }

@@ -100,14 +100,14 @@ __device__ __forceinline__ void mmx_offsets(const MmxPlan &p, int64_t row, int64
 }
 
 template <class T>
-__device__ __forceinline__ void mmx_write(const MmxPlan &p, const int64_t (&oo)[4], const MmxAcc<T> &acc) {
+__device__ __forceinline__ void mmx_write(const MmxPlan &p, const int64_t (&oo)[4], const MmxAcc<T> &acc, bool &flagged) {
   T *cmin = reinterpret_cast<T *>(p.o[0]) + oo[0], *cmax = reinterpret_cast<T *>(p.o[1]) + oo[1];
   long long *imin = reinterpret_cast<long long *>(p.o[2]) + oo[2], *imax = reinterpret_cast<long long *>(p.o[3]) + oo[3];
   if (acc.have) { *cmin = acc.mn; *cmax = acc.mx; *imin = acc.imn; *imax = acc.imx; }
   else {
     *cmin = from_bits<T>(p.obad[0]); *cmax = from_bits<T>(p.obad[1]);
     *imin = (long long)p.obad[2]; *imax = (long long)p.obad[3];
-    if (p.flag) atomicOr(p.flag, 1);
+    flagged = true;
   }
 }
 
@@ -146,11 +146,22 @@ __device__ __forceinline__ void mmx_vec_extremes(const Pack<T> &r, T abad, T &vm
   }
 }
 
+// "a row had no usable element": at most ONE plain store of 1 per warp and launch — p.flag may be a device word or, in
+// the deferred mode, the caller's pinned host int32 (mapped into the device address space), where atomics and a
+// store per flagged row would be slow
+__device__ __forceinline__ void mmx_publish_flag(const MmxPlan &p, bool flagged) {
+  if (flagged && p.flag) {
+    const unsigned m = __activemask();                       // the flagged lanes that got here together: one of them stores
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) *reinterpret_cast<volatile int *>(p.flag) = 1;
+  }
+}
+
 template <class T, bool CHK>
 __global__ void __launch_bounds__(256, 4) minmaximum_warp_kernel(const __grid_constant__ MmxPlan p) {
   const T abad = from_bits<T>(p.abad);
   const int lane = threadIdx.x & 31;
   const int64_t nwork = p.nrows * p.nchunks;
+  bool flagged = false;
   for (int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); w < nwork; w += (int64_t)gridDim.x * 8) {
     const int64_t row = w / p.nchunks, chunk = w - row * p.nchunks;
     int64_t oa = 0;
@@ -203,46 +214,63 @@ __global__ void __launch_bounds__(256, 4) minmaximum_warp_kernel(const __grid_co
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const MmxAcc<T> o = mmx_shfl_down(acc, d); acc.merge(o); }
     if (lane == 0) {
-      if (p.nchunks == 1) { int64_t oo[4]; mmx_offsets(p, row, oa, oo); mmx_write<T>(p, oo, acc); }
+      if (p.nchunks == 1) { int64_t oo[4]; mmx_offsets(p, row, oa, oo); mmx_write<T>(p, oo, acc, flagged); }
       else reinterpret_cast<MmxAcc<T> *>(p.part)[w] = acc;
     }
   }
+  if (flagged && p.flag) *reinterpret_cast<volatile int *>(p.flag) = 1;      // lane 0 only ever sets it: one store per warp
 }
 
-// finishing pass: one CTA per row; threads stride over the chunk partials, then warp shuffles + shared memory
+// finishing pass: one CTA of 1024 threads per row; threads stride over the chunk partials (two independent merges in
+// flight each: a flat 2^28-element ndarray leaves ~9400 partials, and 37 dependent 32-byte loads per thread of a
+// 256-thread CTA cost more than 20 us), then warp shuffles + shared memory
 template <class T>
-__global__ void __launch_bounds__(256) minmaximum_finish_kernel(const __grid_constant__ MmxPlan p) {
-  __shared__ MmxAcc<T> sh[8];
+__global__ void __launch_bounds__(1024) minmaximum_finish_kernel(const __grid_constant__ MmxPlan p) {
+  __shared__ MmxAcc<T> sh[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool flagged = false;
   for (int64_t row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     const MmxAcc<T> *part = reinterpret_cast<const MmxAcc<T> *>(p.part) + row * p.nchunks;
-    MmxAcc<T> acc; acc.init();
-    for (int64_t k = threadIdx.x; k < p.nchunks; k += 256) acc.merge(part[k]);
+    MmxAcc<T> acc, acc2; acc.init(); acc2.init();
+    int64_t k = threadIdx.x;
+    for (; k + 1024 < p.nchunks; k += 2048) {           // ascending chunk order within each accumulator
+      const MmxAcc<T> x = part[k], y = part[k + 1024];
+      acc.merge(x); acc2.merge(y);
+    }
+    if (k < p.nchunks) acc.merge(part[k]);
+    acc.merge(acc2);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) { const MmxAcc<T> o = mmx_shfl_down(acc, d); acc.merge(o); }
     if (lane == 0) sh[wid] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int k = 1; k < 8; k++) acc.merge(sh[k]);
-      int64_t oa, oo[4];
-      mmx_offsets(p, row, oa, oo);
-      mmx_write<T>(p, oo, acc);
+    if (wid == 0) {
+      acc = sh[lane];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) { const MmxAcc<T> o = mmx_shfl_down(acc, d); acc.merge(o); }
+      if (lane == 0) {
+        int64_t oa, oo[4];
+        mmx_offsets(p, row, oa, oo);
+        mmx_write<T>(p, oo, acc, flagged);
+      }
     }
     __syncthreads();
   }
+  if (flagged && p.flag) *reinterpret_cast<volatile int *>(p.flag) = 1;
 }
 
 template <class T, bool CHK>
 __global__ void __launch_bounds__(256) minmaximum_thread_kernel(const __grid_constant__ MmxPlan p) {
   const T abad = from_bits<T>(p.abad);
+  bool flagged = false;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < p.nrows; row += (int64_t)gridDim.x * blockDim.x) {
     int64_t oa, oo[4];
     mmx_offsets(p, row, oa, oo);
     const T *pa = reinterpret_cast<const T *>(p.a) + oa;
     MmxAcc<T> acc; acc.init();
     for (int64_t n = 0; n < p.n; n++) { const T v = pa[n * p.inc_a]; if (mmx_usable<T, CHK>(v, abad)) acc.take(v, n); }
-    mmx_write<T>(p, oo, acc);
+    mmx_write<T>(p, oo, acc, flagged);
   }
+  mmx_publish_flag(p, flagged);
 }
 
 template <class T>
@@ -265,7 +293,7 @@ static int mmx_go(MmxPlan &p, cudaStream_t s, const Err &E) {
     char *base = (char *)scratch(64 + (p.nchunks > 1 ? (size_t)(p.nrows * p.nchunks) * sizeof(MmxAcc<T>) : 0), s);
     if (!base) return E.fail(PDLB200_ECUDA, "minmaximum: cannot allocate scratch");
     p.part = base + 64;
-    if (p.want_flag) { p.flag = (int *)base; PDLB200_CUDA_OK(cudaMemsetAsync(p.flag, 0, sizeof(int), s), E); }
+    if (p.want_flag && !p.flag) { p.flag = (int *)base; PDLB200_CUDA_OK(cudaMemsetAsync(p.flag, 0, sizeof(int), s), E); }
   }
   if (per_thread) {
     int64_t g = (p.nrows + 255) / 256;
@@ -279,7 +307,7 @@ static int mmx_go(MmxPlan &p, cudaStream_t s, const Err &E) {
     else minmaximum_warp_kernel<T, false><<<(int)g, 256, 0, s>>>(p);
     if (p.nchunks > 1) {
       int64_t g2 = p.nrows < cap * 4 ? p.nrows : cap * 4;
-      minmaximum_finish_kernel<T><<<(int)g2, 256, 0, s>>>(p);
+      minmaximum_finish_kernel<T><<<(int)g2, 1024, 0, s>>>(p);
       note_launch("minmaximum");
     }
   }
@@ -321,6 +349,9 @@ int launch_minmaximum(const pdlb200_trans *t, const Err &E) {
   // "no usable element" can only happen with BAD inputs, NaNs (floating point) or n == 0
   const bool may_flag = p.badmode || p.n == 0 || t->datatype >= PDLB200_F;
   p.want_flag = may_flag;
+  // deferred mode: the kernels store straight into the caller's pinned int32 (already 0) — no memset, no copy, no sync
+  const bool defer = may_flag && (t->tflags & PDLB200_TRANS_DEFER_ANYBAD);
+  if (defer) p.flag = reinterpret_cast<int *>(t->anybad);
   int rc;
   switch (t->datatype) {
     case PDLB200_SB: rc = mmx_go<int8_t>(p, s, E); break;   case PDLB200_B:  rc = mmx_go<uint8_t>(p, s, E); break;
@@ -333,10 +364,7 @@ int launch_minmaximum(const pdlb200_trans *t, const Err &E) {
   }
   if (rc) return rc;
   if (may_flag) {
-    if (t->tflags & PDLB200_TRANS_DEFER_ANYBAD) {   // pinned destination: no host round trip inside the call
-      PDLB200_CUDA_OK(cudaMemcpyAsync(t->anybad, scratch(64, s), sizeof(int), cudaMemcpyDeviceToHost, s), E);
-      return PDLB200_OK;
-    }
+    if (defer) return PDLB200_OK;
     int host = 0;
     PDLB200_CUDA_OK(cudaMemcpyAsync(&host, scratch(64, s), sizeof(int), cudaMemcpyDeviceToHost, s), E);
     PDLB200_CUDA_OK(cudaStreamSynchronize(s), E);

@@ -49,3 +49,17 @@ def test_engine_refuses_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(P.PDLError):
         P.CudaEngine()
+
+
+def test_loader_refuses_a_library_built_from_other_sources(monkeypatch):
+    """The prebuilt .so travels to the GPU box as a file: the loader compares the id compiled into it
+    (pdlb200_build_id) with the hash of the sources next to it and refuses a mismatch instead of testing a stale build."""
+    from pdl_b200 import build
+    lib = _abi.load()
+    assert lib.pdlb200_build_id().decode() == build.source_id()
+    monkeypatch.setattr(_abi, "_lib", None)
+    monkeypatch.setattr(build, "source_id", lambda: "0" * 16)
+    with pytest.raises(_abi.LibraryMissing, match="built from other sources"):
+        _abi.load()
+    monkeypatch.setenv("PDLB200_SKIP_BUILD_ID", "1")
+    assert _abi.load() is not None

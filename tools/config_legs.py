@@ -162,3 +162,34 @@ def cfg4(eng, dev, reps=4):
     res["ms"], res["tflops"] = res["dmma_8192"]["ms"], res["dmma_8192"]["tflops"]
     res["verified"] = all(v["verified"] for v in res.values() if isinstance(v, dict))
     return res
+
+
+def next_rows(eng, dev, peak, reps=20):
+    """Two of §8's "next" rows under the driver's clock: the single-pass scan of ONE long row (cumusumover of 2^28
+    floats) and minmaximum of a flat 2^28-float ndarray (the body of `minmax`), both verified against torch."""
+    g = torch.Generator(device=dev).manual_seed(6)
+    n = 2 ** 28
+    x = torch.randint(-8, 9, (n,), device=dev, generator=g).float()
+    px = wrap(eng, x, T.F, [n])
+    out = P.PDL.empty(T.F, [n], eng)
+    c0 = eng.launch_count()
+    P.run_op("cumusumover", [px], [out])
+    launches = eng.launch_count() - c0
+    ms = timeit(lambda: P.run_op("cumusumover", [px], [out]), reps)
+    got = torch.as_tensor(type("C", (), {"__cuda_array_interface__": {"shape": (n,), "typestr": "<f4",
+                          "data": (out.store.ptr, False), "version": 3}})(), device=dev)
+    ok = bool(torch.equal(got, torch.cumsum(x.double(), 0).float()))        # integer-valued: every partial sum is exact
+    res = {"workload": "next rows: cumusumover float[2^28] (one row) and minmaximum float[2^28] (flat)",
+           "cumusumover_1d": {"ms": ms, "gbs": 8 * n / ms / 1e6, "frac": 8 * n / ms / 1e6 / peak, "launches": int(launches),
+                              "kernel": eng.last_kernel(), "verified": ok}}
+    del got, out
+    x[123456789] = 50.0
+    x[987654] = -50.0
+    outs = [P.PDL.empty(T.F, [], eng), P.PDL.empty(T.F, [], eng), P.PDL.empty(T.IND, [], eng), P.PDL.empty(T.IND, [], eng)]
+    prep = P.prepare_op("minmaximum", [px], outs)
+    ms = timeit(prep, reps)
+    vals = [o.to_numpy().item() for o in prep()]
+    res["minmaximum_flat"] = {"ms": ms, "gbs": 4 * n / ms / 1e6, "frac": 4 * n / ms / 1e6 / peak, "kernel": eng.last_kernel(),
+                              "verified": vals == [-50.0, 50.0, 987654, 123456789]}
+    res["verified"] = res["cumusumover_1d"]["verified"] and res["minmaximum_flat"]["verified"]
+    return res
