@@ -43,15 +43,49 @@ __device__ __noinline__ T mm_nan_elem(const T *a, const T *b, int64_t tn, int64_
   return cc;
 }
 
+// One output element of a BAD-mode product exactly as the reference computes it (Primitive.pd:224-244), x86 NaN rules
+// at every step: run only for outputs of the fast BAD path that ended up NaN (their value, not their state, is what
+// the fast path's plain arithmetic cannot reproduce).
+template <class T>
+__device__ __noinline__ T mm_bad_elem(const T *a, const T *b, int64_t tn, int64_t iat, int64_t ibt, T abad, T bbad, T cbad,
+                                      bool abadnan, bool bbadnan, bool cbadnan, int64_t tsiz) {
+  T cc = T(0);
+  for (int64_t ts = 0; ts < tn; ts += tsiz) {
+    if (is_bad(cc, cbad, cbadnan)) continue;
+    T run = cc;
+    bool isbad = false;
+    const int64_t te = ts + tsiz < tn ? ts + tsiz : tn;
+    for (int64_t t = ts; t < te; t++) {
+      const T x = a[t * iat], y = b[t * ibt];
+      if (is_bad(x, abad, abadnan) || is_bad(y, bbad, bbadnan)) { isbad = true; break; }
+      const T m = x86_nan2(x, y, x * y);
+      run = x86_nan2(run, m, run + m);
+    }
+    cc = isbad ? cbad : run;
+  }
+  return cc;
+}
+
+// BAD mode (Primitive.pd:227,235,241), per output and per t-tile of TSIZ elements: at the tile start the running value
+// is tested against c's badvalue — if it IS bad the output stops with that value (state 1); a BAD a(t,h) or b(w,t)
+// inside the tile makes the output BAD (state 2); either way it stays stopped.  Round 2: the kernel no longer tests a
+// flag per multiply-add.  Staging leaves ONE flag per (row, sub-tile) of a and per (column, 4 k) of b; a thread
+// updates the states of its 4x4 outputs once per sub-tile (16-bit masks), and then runs the sub-tile's multiply-adds
+// unconditionally (nothing stopped: the common case), not at all (everything stopped: the common case once BAD values
+// are frequent — a CTA whose outputs have all stopped leaves the t loop), or per output (mixed).  Float/double run plain
+// multiply + add here as in good mode; outputs that end up NaN are recomputed by mm_bad_elem.
 template <class T, bool BAD>
 __global__ void __launch_bounds__(256)
 mm_exact_kernel(const __grid_constant__ MmPlan p) {
   using A = typename mm_acc<T>::type;  // wrap-around accumulator; low bits == the reference's `cc += a*b` in T
   constexpr int64_t TSIZ = 8 * sizeof(double) / sizeof(T);  // the reference's tile edge (Primitive.pd:212)
+  constexpr int SUB = TSIZ < MM_BK ? (int)TSIZ : MM_BK;      // state updates per staged chunk: every SUB k
+  constexpr int NSUB = MM_BK / SUB;
   __shared__ T sA[MM_BK][MM_BM + 1];
   __shared__ T sB[MM_BK][MM_BN + 1];
-  __shared__ unsigned char fA[BAD ? MM_BK : 1][BAD ? MM_BM + 1 : 1];  // BAD flags of the staged tiles
-  __shared__ unsigned char fB[BAD ? MM_BK : 1][BAD ? MM_BN + 1 : 1];
+  __shared__ unsigned char rfA[BAD ? NSUB : 1][BAD ? MM_BM : 1];  // a BAD a(t,h) in sub-tile s of row h
+  __shared__ unsigned char cfB[BAD ? 4 : 1][BAD ? MM_BN : 1];     // a BAD b(w,t) among k in [4q, 4q+4) of column w
+  __shared__ int s_live[2];         // "some output of this CTA is still live", double-buffered by chunk parity
 
   int64_t oa = 0, ob = 0, oc = 0;
   {
@@ -69,76 +103,160 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
   const T abad = from_bits<T>(p.abad), bbad = from_bits<T>(p.bbad), cbad = from_bits<T>(p.cbad);
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  const int lane = threadIdx.x & 31;
   const int64_t h0 = (int64_t)blockIdx.y * MM_BM, w0 = (int64_t)blockIdx.x * MM_BN;
 
   A acc[MM_TM][MM_TN];
-  // BAD mode (Primitive.pd:227,235,241): 0 live; 1 stopped because cc itself tested BAD at a t-tile start
-  // (value kept); 2 stopped because a BAD a/b was met (c = c's badvalue).  Either way it stays stopped.
-  unsigned char frozen[MM_TM][MM_TN];
+  unsigned fz1 = 0, fz2 = 0;           // bit i*4+j: output (i,j) stopped in state 1 / state 2
 #pragma unroll
   for (int i = 0; i < MM_TM; i++)
 #pragma unroll
-    for (int j = 0; j < MM_TN; j++) { acc[i][j] = A(0); frozen[i][j] = 0; }
+    for (int j = 0; j < MM_TN; j++) acc[i][j] = A(0);
 
-  for (int64_t t0 = 0; t0 < p.T; t0 += MM_BK) {
+  if (BAD && threadIdx.x == 0) s_live[0] = 0;
+  int chunk = 0;
+  for (int64_t t0 = 0; t0 < p.T; t0 += MM_BK, chunk++) {
     // stage A[h0..h0+BM) x [t0..t0+BK)  and  B[t0..t0+BK) x [w0..w0+BN); threads run along t for A
     // and along w for B, the unit-stride dims of PDL's default layout
-    for (int e = threadIdx.x; e < MM_BM * MM_BK; e += 256) {
+#pragma unroll
+    for (int r = 0; r < MM_BM * MM_BK / 256; r++) {
+      const int e = threadIdx.x + 256 * r;
       const int k = e % MM_BK, m = e / MM_BK;
       const int64_t h = h0 + m, tt_ = t0 + k;
-      T v = T(0); unsigned char f = 0;
+      T v = T(0); bool f = false;
       if (h < p.H && tt_ < p.T) {
         v = Ap[tt_ * p.iat + h * p.iah];
         if (BAD) f = is_bad(v, abad, p.abadnan != 0);
       }
       sA[k][m] = v;
-      if (BAD) fA[k][m] = f;
-    }
-    for (int e = threadIdx.x; e < MM_BK * MM_BN; e += 256) {
-      const int n = e % MM_BN, k = e / MM_BN;
-      const int64_t w = w0 + n, tt_ = t0 + k;
-      T v = T(0); unsigned char f = 0;
-      if (w < p.W && tt_ < p.T) {
-        v = Bp[w * p.ibw + tt_ * p.ibt];
-        if (BAD) f = is_bad(v, bbad, p.bbadnan != 0);
+      if (BAD) {
+        // 16 consecutive lanes hold the 16 k of one row: the row's flags come out of one ballot
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if ((k % SUB) == 0) rfA[k / SUB][m] = ((bal >> ((lane & 16) + k)) & ((1u << SUB) - 1u)) != 0;
       }
-      sB[k][n] = v;
-      if (BAD) fB[k][n] = f;
+    }
+    {
+      const int n = threadIdx.x % MM_BN, q = threadIdx.x / MM_BN;      // this thread: column n, k in [4q, 4q+4)
+      const int64_t w = w0 + n;
+      bool f = false;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int k = 4 * q + r;
+        const int64_t tt_ = t0 + k;
+        T v = T(0);
+        if (w < p.W && tt_ < p.T) {
+          v = Bp[w * p.ibw + tt_ * p.ibt];
+          if (BAD) f = f || is_bad(v, bbad, p.bbadnan != 0);
+        }
+        sB[k][n] = v;
+      }
+      if (BAD) cfB[q][n] = f;
     }
     __syncthreads();
+    if (BAD && threadIdx.x == 0) s_live[(chunk + 1) & 1] = 0;    // read last after the previous chunk's second barrier
     const int kmax = (p.T - t0) < MM_BK ? (int)(p.T - t0) : MM_BK;
+    if constexpr (BAD) {
 #pragma unroll
-    for (int k = 0; k < MM_BK; k++) {
-      if (k < kmax) {
-        T av[MM_TM], bv[MM_TN];
-        unsigned char af[MM_TM], bf[MM_TN];
+      for (int sub = 0; sub < NSUB; sub++) {
+        if (sub * SUB >= kmax) break;
+        unsigned fz = fz1 | fz2;
+        if (fz != 0xffffu) {
+          if (((t0 + sub * SUB) % TSIZ) == 0) {
+            // the reference re-tests cc against c's badvalue at every t-tile start (Primitive.pd:227)
 #pragma unroll
-        for (int i = 0; i < MM_TM; i++) { av[i] = sA[k][ty * MM_TM + i]; if (BAD) af[i] = fA[k][ty * MM_TM + i]; }
+            for (int i = 0; i < MM_TM; i++)
 #pragma unroll
-        for (int j = 0; j < MM_TN; j++) { bv[j] = sB[k][tx * MM_TN + j]; if (BAD) bf[j] = fB[k][tx * MM_TN + j]; }
+              for (int j = 0; j < MM_TN; j++)
+                if (!((fz >> (i * 4 + j)) & 1u) && is_bad((T)acc[i][j], cbad, p.cbadnan != 0)) fz1 |= 1u << (i * 4 + j);
+          }
+          unsigned rf = 0, cf = 0;
 #pragma unroll
-        for (int i = 0; i < MM_TM; i++)
+          for (int i = 0; i < MM_TM; i++) rf |= (unsigned)rfA[sub][ty * MM_TM + i] << i;
 #pragma unroll
           for (int j = 0; j < MM_TN; j++) {
-            if (BAD) {
-              // the reference re-tests cc against c's badvalue at every t-tile start (Primitive.pd:227)
-              if (((t0 + k) % TSIZ) == 0 && !frozen[i][j] && is_bad((T)acc[i][j], cbad, p.cbadnan != 0)) frozen[i][j] = 1;
-              if (!frozen[i][j] && (af[i] | bf[j])) frozen[i][j] = 2;
-              if (frozen[i][j]) continue;
-            }
-            if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
-            else if constexpr (BAD) {  // two roundings (and x86 NaN rules), as on the reference's x86-64 build
-              const T m = x86_nan2(av[i], bv[j], av[i] * bv[j]);
-              acc[i][j] = x86_nan2(acc[i][j], m, acc[i][j] + m);
-            } else {
-              // good mode: plain multiply then add (two roundings, -fmad=false).  A NaN is sticky in a sum, so its
-              // x86 sign/payload rules are applied afterwards, only to the outputs that ended up NaN (mm_nan_elem)
-              acc[i][j] = acc[i][j] + av[i] * bv[j];
+            unsigned c4 = 0;
+#pragma unroll
+            for (int q = sub * SUB / 4; q < (sub + 1) * SUB / 4; q++) c4 |= cfB[q][tx * MM_TN + j];
+            cf |= c4 << j;
+          }
+          if (rf | cf) {
+#pragma unroll
+            for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+              for (int j = 0; j < MM_TN; j++)
+                if ((((rf >> i) | (cf >> j)) & 1u) && !((fz1 >> (i * 4 + j)) & 1u)) fz2 |= 1u << (i * 4 + j);
+          }
+          fz = fz1 | fz2;
+        }
+        if (fz == 0xffffu) continue;                       // every output of this thread has stopped
+        const int kend = (kmax - sub * SUB) < SUB ? kmax - sub * SUB : SUB;
+        if (fz == 0) {
+#pragma unroll
+          for (int kk = 0; kk < SUB; kk++) {
+            if (kk < kend) {
+              const int k = sub * SUB + kk;
+              T av[MM_TM], bv[MM_TN];
+#pragma unroll
+              for (int i = 0; i < MM_TM; i++) av[i] = sA[k][ty * MM_TM + i];
+#pragma unroll
+              for (int j = 0; j < MM_TN; j++) bv[j] = sB[k][tx * MM_TN + j];
+#pragma unroll
+              for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+                for (int j = 0; j < MM_TN; j++) {
+                  if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
+                  else acc[i][j] = acc[i][j] + av[i] * bv[j];
+                }
             }
           }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < SUB; kk++) {
+            if (kk < kend) {
+              const int k = sub * SUB + kk;
+              T av[MM_TM], bv[MM_TN];
+#pragma unroll
+              for (int i = 0; i < MM_TM; i++) av[i] = sA[k][ty * MM_TM + i];
+#pragma unroll
+              for (int j = 0; j < MM_TN; j++) bv[j] = sB[k][tx * MM_TN + j];
+#pragma unroll
+              for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+                for (int j = 0; j < MM_TN; j++) {
+                  if ((fz >> (i * 4 + j)) & 1u) continue;
+                  if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
+                  else acc[i][j] = acc[i][j] + av[i] * bv[j];
+                }
+            }
+          }
+        }
       }
+      // a CTA whose outputs have all stopped has nothing left to do
+      if ((fz1 | fz2) != 0xffffu) s_live[chunk & 1] = 1;
+      __syncthreads();
+      if (!s_live[chunk & 1]) break;
+    } else {
+#pragma unroll
+      for (int k = 0; k < MM_BK; k++) {
+        if (k < kmax) {
+          T av[MM_TM], bv[MM_TN];
+#pragma unroll
+          for (int i = 0; i < MM_TM; i++) av[i] = sA[k][ty * MM_TM + i];
+#pragma unroll
+          for (int j = 0; j < MM_TN; j++) bv[j] = sB[k][tx * MM_TN + j];
+#pragma unroll
+          for (int i = 0; i < MM_TM; i++)
+#pragma unroll
+            for (int j = 0; j < MM_TN; j++) {
+              if constexpr (tt<T>::is_int) acc[i][j] += (A)av[i] * (A)bv[j];
+              // good mode: plain multiply then add (two roundings, -fmad=false).  A NaN is sticky in a sum, so its
+              // x86 sign/payload rules are applied afterwards, only to the outputs that ended up NaN (mm_nan_elem)
+              else acc[i][j] = acc[i][j] + av[i] * bv[j];
+            }
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < MM_TM; i++)
@@ -147,8 +265,15 @@ mm_exact_kernel(const __grid_constant__ MmPlan p) {
       const int64_t h = h0 + ty * MM_TM + i, w = w0 + tx * MM_TN + j;
       if (h < p.H && w < p.W) {
         T out = (T)acc[i][j];
-        if (BAD && frozen[i][j] == 2) out = cbad;
-        if constexpr (!BAD && !tt<T>::is_int) { if (out != out) out = mm_nan_elem<T>(Ap + h * p.iah, Bp + w * p.ibw, p.T, p.iat, p.ibt); }
+        if (BAD && ((fz2 >> (i * 4 + j)) & 1u)) out = cbad;
+        if constexpr (!tt<T>::is_int) {
+          if (out != out) {
+            if constexpr (BAD)
+              out = mm_bad_elem<T>(Ap + h * p.iah, Bp + w * p.ibw, p.T, p.iat, p.ibt, abad, bbad, cbad, p.abadnan != 0,
+                                   p.bbadnan != 0, p.cbadnan != 0, TSIZ);
+            else out = mm_nan_elem<T>(Ap + h * p.iah, Bp + w * p.ibw, p.T, p.iat, p.ibt);
+          }
+        }
         Cp[w * p.icw + h * p.ich] = out;
       }
     }

@@ -233,6 +233,34 @@ def test_matmult_bad_and_batched(engines):
     assert_same("matmult-transposed-views", outs[0], outs[1])
 
 
+@pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
+def test_matmult_bad_states(engines, t):
+    """BAD-mode matmult (Primitive.pd:224-244) on the flag-per-sub-tile kernel: outputs stop either because the running
+    value itself equals c's badvalue at a t-tile start (8/16-bit sums wrap onto it all the time) or because a BAD
+    a/b element sits in the tile; sparse BAD values (most threads never stop), dense ones (whole CTAs stop early),
+    BAD values only in a, only in b, ragged sizes around the reference's tile edges, NaN as the badvalue."""
+    rng = np.random.default_rng(1350 + t)
+    dt = T.NP_DTYPE[t]
+    bad = np.array(T.DEFAULT_BAD[t]).astype(dt)
+    for (h, tt, w), dens in (((70, 200, 90), (0.0005, 0.0005)), ((64, 640, 64), (0.0, 0.0)), ((130, 97, 67), (0.02, 0.0)),
+                             ((33, 129, 140), (0.0, 0.02)), ((96, 80, 96), (0.3, 0.3)), ((5, 1, 3), (0.2, 0.2))):
+        a, b = rand_array(rng, t, (h, tt), "mixed"), rand_array(rng, t, (tt, w), "mixed")
+        a[rng.random(a.shape) < dens[0]] = bad
+        b[rng.random(b.shape) < dens[1]] = bad
+        (ga, oa), (gb, ob) = both(engines, a, t, True), both(engines, b, t, True)
+        assert_same(f"matmult-badstates-{T.NAMES[t]}-{h}x{tt}x{w}", P.matmult(ga, gb), P.matmult(oa, ob))
+    if t in (T.F, T.D):
+        a, b = rand_array(rng, t, (70, 150), "small"), rand_array(rng, t, (150, 66), "small")
+        a[rng.random(a.shape) < 0.002] = np.nan            # BAD (the badvalue is NaN) ...
+        b[3, 5] = np.inf; b[4, 5] = -np.inf                 # ... and NaNs born in the sum: the running value turns BAD
+        res = []
+        for e in engines:
+            pa, pb = P.PDL.from_numpy(a, t, e), P.PDL.from_numpy(b, t, e)
+            pa.set_badvalue(float("nan")); pa.badflag = True
+            res.append(P.matmult(pa, pb))
+        assert_same(f"matmult-badstates-nanbad-{T.NAMES[t]}", res[0], res[1], nan_equal=True)
+
+
 def test_matmult_default_path_double(engines):
     """Default double path (tensor-core tiles when eligible): exactly representable inputs make
     every product and partial sum exact, so the result must be BIT-EXACT whatever the order;
