@@ -411,28 +411,49 @@ __global__ void __launch_bounds__(OP_THREADS, 1) scan_onepass_kernel(const __gri
   }
 }
 
+// rows whose length is not a whole number of 16-byte vectors: the (< 16 bytes of) elements after the last vector,
+// one thread per row, carried on from the row's inclusive prefix — the P descriptor of the row's last tile
+template <class T, class O, bool PROD>
+__global__ void scan_onepass_tail_kernel(const __grid_constant__ OpPlan p, int64_t n_all, int64_t nrows) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  const T abad = from_bits<T>(p.abad);
+  const O bbad = from_bits<O>(p.bbad);
+  O carry;
+  OpDesc<O>::get(p.desc, row * p.tpr + p.tpr - 1, carry);
+  const T *a = reinterpret_cast<const T *>(p.a) + row * p.sa;
+  O *b = reinterpret_cast<O *>(p.b) + row * p.sb;
+  for (int64_t k = p.n; k < n_all; k++) {
+    const T v = a[k];
+    if (p.badmode && is_bad(v, abad, p.abadnan != 0)) { b[k] = bbad; continue; }
+    carry = scan_op<O, PROD>(carry, (O)v);
+    b[k] = carry;
+  }
+}
+
 // Returns true when the launch was taken (rc holds the status); false: not eligible, use the three-pass path.
 template <class T, class O, bool PROD>
 static bool scan_onepass_try(const ScPlan &p, cudaStream_t s, const char *name, const Err &E, int *rc) {
   if constexpr (sizeof(T) != sizeof(O) || sizeof(T) < 4) return false;
   else {
-    static const bool off = [] { const char *e = getenv("PDLB200_SCAN"); return e && !strcmp(e, "3pass"); }();
-    if (off) return false;
+    { const char *e = getenv("PDLB200_SCAN"); if (e && !strcmp(e, "3pass")) return false; }
     constexpr int64_t TE = OP_TILE_BYTES / (int64_t)sizeof(T);
+    constexpr int64_t VEC = 16 / (int64_t)sizeof(T);
     if (p.inc_a != 1 || p.inc_b != 1 || p.nd > 1) return false;
-    if ((p.n * (int64_t)sizeof(T)) % 16 != 0 || p.n < 16 * TE) return false;
+    const int64_t nmain = p.n - p.n % VEC;          // whole 16-byte vectors: the bulk copies' granularity; the rest is the tail
+    if (nmain < 16 * TE) return false;
     if (((uintptr_t)p.a & 15) || ((uintptr_t)p.b & 15)) return false;
     int64_t sa = 0, sb = 0;
     if (p.nd == 1) {
       sa = p.sa[0]; sb = p.sb[0];
       if ((sa * (int64_t)sizeof(T)) % 16 != 0 || (sb * (int64_t)sizeof(O)) % 16 != 0 || sa < 0 || sb < 0) return false;
     } else if (p.nrows != 1) return false;
-    const int64_t tpr = (p.n + TE - 1) / TE;
+    const int64_t tpr = (nmain + TE - 1) / TE;
     const int64_t ntiles = tpr * p.nrows;
     if (ntiles < 2 * (int64_t)sm_count() || ntiles > (1ll << 30)) return false;
     OpPlan q;
     memset(&q, 0, sizeof q);
-    q.a = p.a; q.b = p.b; q.n = p.n; q.tpr = tpr; q.ntiles = ntiles; q.sa = sa; q.sb = sb;
+    q.a = p.a; q.b = p.b; q.n = nmain; q.tpr = tpr; q.ntiles = ntiles; q.sa = sa; q.sb = sb;
     q.abad = p.abad; q.bbad = p.bbad; q.abadnan = p.abadnan; q.badmode = p.badmode;
     const size_t dbytes = (size_t)ntiles * OpDesc<O>::BYTES;
     char *scr = (char *)scratch(dbytes + 16, s);
@@ -467,6 +488,10 @@ static bool scan_onepass_try(const ScPlan &p, cudaStream_t s, const char *name, 
       else scan_onepass_kernel<T, O, PROD, 0><<<(int)g, OP_THREADS, OP_SLOTS * OP_TILE_BYTES, s>>>(q);
     }
     note_launch(name);
+    if (nmain < p.n) {
+      scan_onepass_tail_kernel<T, O, PROD><<<(unsigned)((p.nrows + 127) / 128), 128, 0, s>>>(q, p.n, p.nrows);
+      note_launch(name);
+    }
 #ifdef PDLB200_SCAN_PROF
     if (getenv("PDLB200_SCAN_PROF_PRINT")) {
       static long long host[16 * 1024];

@@ -123,8 +123,9 @@ def test_cfg5_full_array_sum_max(cuda_engine):
 
 
 def test_long_row_scan_chunked(cuda_engine):
-    """cumusumover / cumuprodover over one very long row (the chunked three-pass scan, chunk > 4096):
-    integer-valued floats make every partial sum exact, so any association order must agree bitwise."""
+    """cumusumover over one very long row whose length is NOT a whole number of 16-byte vectors (single-pass scan of
+    the vectors + the tail kernel carrying on from the row's last descriptor), and two rows with an odd pitch (the
+    chunked three-pass scan): integer-valued floats make every partial sum exact, so any order must agree bitwise."""
     g = torch.Generator(device="cuda").manual_seed(17)
     n = 2**27 + 12345
     x = torch.randint(-8, 9, (n,), device="cuda", generator=g).float()
@@ -146,12 +147,14 @@ def test_long_row_scan_chunked(cuda_engine):
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("mode", ["onepass", "3pass"])
 @pytest.mark.parametrize("case", ["float-2rows-bad", "double-prod", "int64-sum", "int32-3rows-tail"])
-def test_lookback_scan_variants(cuda_engine, case):
-    """Long-row scans (the chunked three-pass scheme: chunk totals, exclusive scan of the totals, scan with carry-in;
-    the case names date from the look-back experiments recorded in DESIGN.md §4): BAD elements, several rows,
-    products, 64-bit accumulators, rows ending inside a vector — against torch's cumsum/cumprod on inputs whose
-    partial results are exactly representable."""
+def test_lookback_scan_variants(cuda_engine, case, mode, monkeypatch):
+    """Long-row scans through BOTH schemes — the single-pass look-back kernel (scan_onepass.cuh) and, with
+    PDLB200_SCAN=3pass, the chunked three-pass scheme it falls back to (chunk totals, exclusive scan of the totals,
+    scan with carry-in): BAD elements, several rows, products, 64-bit accumulators, rows ending inside a tile —
+    against torch's cumsum/cumprod on inputs whose partial results are exactly representable."""
+    monkeypatch.setenv("PDLB200_SCAN", mode)
     g = torch.Generator(device="cuda").manual_seed(23)
     if case == "float-2rows-bad":
         n = 2**22 + 8                                   # rows stay 16-byte aligned
@@ -185,7 +188,7 @@ def test_lookback_scan_variants(cuda_engine, case):
         assert torch.equal(got, torch.cumsum(y.view(3, n).long(), 1).int())
 
 
-@pytest.mark.parametrize("case", ["float-1row", "float-1row-bad", "ll-to-double", "double-4rows-strided", "prod-int32"])
+@pytest.mark.parametrize("case", ["float-1row", "float-1row-bad", "float-odd-tail-bad", "ll-to-double", "double-4rows-strided", "prod-int32"])
 def test_onepass_scan(cuda_engine, case):
     """The single-pass look-back scan (scan_onepass.cuh): ONE launch for rows cut into 48 KB tiles, against torch on
     exactly representable data; the same inputs through the three-pass path must give the same bytes."""
@@ -196,8 +199,8 @@ def test_onepass_scan(cuda_engine, case):
         out = fn()
         return out, cuda_engine.launch_count() - c0
 
-    if case in ("float-1row", "float-1row-bad"):
-        n = 2**26 + 4 * 777                                   # last tile partial
+    if case in ("float-1row", "float-1row-bad", "float-odd-tail-bad"):
+        n = 2**26 + 4 * 777 + (3 if "odd" in case else 0)     # last tile partial; odd: 3 elements after the last vector
         y = torch.randint(-8, 9, (n,), device="cuda", generator=g).float()
         py = wrap(cuda_engine, y, T.F, [n])
         want = y.double()
@@ -206,8 +209,10 @@ def test_onepass_scan(cuda_engine, case):
             y[bad] = -9999.0
             py.set_badvalue(-9999.0).set_badflag(True)
             want = torch.where(bad, torch.zeros_like(want), want)
+        if "odd" in case:
+            y[n - 2] = -9999.0; bad[n - 2] = True; want[n - 2] = 0.0      # a BAD element inside the tail
         out, nl = run(lambda: ufunc.cumusumover(py))
-        assert nl == 1, nl
+        assert nl == (2 if "odd" in case else 1), nl
         want = torch.cumsum(want, 0).float()
         if case.endswith("bad"):
             want[bad] = float(out.badvalue)
