@@ -265,10 +265,15 @@ __device__ __forceinline__ void ew_compute_store(const EwPlan &p, const Pack<TI>
       // harmless operand pair (1 op 1) first, then put the output badvalue in their place
       Pack<TI> ma; Pack<TB> mb;
       bool bad[VEC];
+      // one compare per operand element whatever the mode: against the badvalue, against the element itself when the
+      // badvalue is NaN (bad <=> the element is not equal to itself), against NaN when the operand is not checked
+      const bool nan_a = p.badchk[0] && p.badnan[0] != 0, nan_b = NIN > 1 && p.badchk[1] && p.badnan[1] != 0;
+      const TI cmp_a = p.badchk[0] ? abad : TI(NAN);
+      const TB cmp_b = (NIN > 1 && p.badchk[1]) ? bbad : TB(NAN);
 #pragma unroll
       for (int k = 0; k < VEC; k++) {
-        bad[k] = p.badchk[0] && is_bad(ra.e[k], abad, p.badnan[0] != 0);
-        if (NIN > 1) bad[k] = bad[k] || (p.badchk[1] && is_bad(rb.e[k], bbad, p.badnan[1] != 0));
+        bad[k] = (ra.e[k] == (nan_a ? ra.e[k] : cmp_a)) != nan_a;
+        if (NIN > 1) bad[k] = bad[k] || ((rb.e[k] == (nan_b ? rb.e[k] : cmp_b)) != nan_b);
         ma.e[k] = bad[k] ? TI(1) : ra.e[k];
         mb.e[k] = (NIN > 1) ? (bad[k] ? TB(1) : rb.e[k]) : TB(1);
       }
