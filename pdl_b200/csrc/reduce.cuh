@@ -322,6 +322,17 @@ template <class T, bool ISMAX> struct RMinMaxInt {
     if constexpr (tt<T>::is_uns) return ISMAX ? T(0) : T(~T(0));
     else { using U = typename std::make_unsigned<T>::type; const T mx = (T)(U(~U(0)) >> 1); return ISMAX ? (T)(-mx - 1) : mx; }
   }
+  // the OTHER extreme of the type.  When the badvalue is that one (minimum of a signed row, maximum of an unsigned one,
+  // with the default badvalues), adding (max) or subtracting (min) one in every lane, wrapping, turns exactly the BAD
+  // lanes into the identity and keeps the order of all others: again no mask (BADK 4); lift() undoes the shift.
+  static __device__ __forceinline__ T anti_identity() {
+    if constexpr (tt<T>::is_uns) return ISMAX ? T(~T(0)) : T(0);
+    else { using U = typename std::make_unsigned<T>::type; const T mx = (T)(U(~U(0)) >> 1); return ISMAX ? mx : (T)(-mx - 1); }
+  }
+  static __device__ __forceinline__ uint32_t shift_packed(uint32_t w) {
+    if constexpr (sizeof(T) == 1) return ISMAX ? __vadd4(w, 0x01010101u) : __vsub4(w, 0x01010101u);
+    else return ISMAX ? __vadd2(w, 0x00010001u) : __vsub2(w, 0x00010001u);
+  }
   static __device__ __forceinline__ T pick(T a, T b) { return ISMAX ? (b > a ? b : a) : (b < a ? b : a); }
   static __device__ __forceinline__ uint32_t pick_packed(uint32_t a, uint32_t b) {
     if constexpr (sizeof(T) == 1) {
@@ -335,7 +346,7 @@ template <class T, bool ISMAX> struct RMinMaxInt {
     if constexpr (kPack) x.pk = swar_splat<T>(identity());
     return x;
   }
-  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.cur = pick(x.cur, v); x.any = 1; }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.cur = pick(x.cur, v); x.any |= 1; }
   template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
     const uint32_t badw = swar_splat<T>(abad), identw = swar_splat<T>(identity());
     const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
@@ -348,6 +359,11 @@ template <class T, bool ISMAX> struct RMinMaxInt {
 #pragma unroll
       for (int i = 0; i < 4; i++) { x.pk = pick_packed(x.pk, w[i]); good |= (w[i] != badw); }
       x.any |= good;
+    } else if constexpr (BADK == 4) {
+      int32_t good = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) { x.pk = pick_packed(x.pk, shift_packed(w[i])); good |= (w[i] != badw); }
+      x.any |= good | 2;                       // bit 1: the lanes of pk are in the shifted domain
     } else {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -360,10 +376,18 @@ template <class T, bool ISMAX> struct RMinMaxInt {
   }
   static constexpr bool kBadIdentity = kPack;   // rd_row may pick BADK 3 when the badvalue equals identity()
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) {
-    Acc x; x.cur = l.cur; x.any = l.any; x.pad = 0; x.pad2 = 0;
+    Acc x; x.cur = l.cur; x.any = l.any & 1; x.pad = 0; x.pad2 = 0;
     if constexpr (kPack) {
+      const bool shifted = (l.any & 2) != 0;
 #pragma unroll
-      for (int k = 0; k < (int)(4 / sizeof(T)); k++) x.cur = pick(x.cur, (T)(l.pk >> (8 * sizeof(T) * k)));
+      for (int k = 0; k < (int)(4 / sizeof(T)); k++) {
+        T v = (T)(l.pk >> (8 * sizeof(T) * k));
+        if (shifted) {
+          if (v == identity()) continue;       // only BAD lanes (or none at all) end up on the identity
+          v = ISMAX ? (T)(v - 1) : (T)(v + 1);
+        }
+        x.cur = pick(x.cur, v);
+      }
     }
     return x;
   }
@@ -483,14 +507,15 @@ template <class T, bool GOOD> struct RCount {
 };
 
 // ---- row walk -------------------------------------------------------------------
-// BADK: 0 = no BAD test (good-mode code path), 1 = BAD iff v == badvalue, 2 = BAD iff v is NaN
+// BADK: 0 = no BAD test (good-mode code path), 1 = BAD iff v == badvalue, 2 = BAD iff v is NaN,
+// 3 / 4 = the badvalue is the packed min/max reducer's identity / the other extreme of the type (no mask needed)
 // (per-ndarray NaN badvalue).  Hoisted to a template so the hot loop pays one compare at most.
 template <class R, class = void> struct rd_kbadident { static constexpr bool value = false; };
 template <class R> struct rd_kbadident<R, std::void_t<decltype(R::kBadIdentity)>> { static constexpr bool value = R::kBadIdentity; };
 
 template <class R, class T, int BADK>
 __device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad) {
-  if constexpr (BADK == 1 || BADK == 3) { if (v == abad) return; }
+  if constexpr (BADK == 1 || BADK == 3 || BADK == 4) { if (v == abad) return; }
   if constexpr (BADK == 2) { if (t_isnan(v)) return; }
   R::lpush(loc, v, rel);
 }
@@ -555,6 +580,7 @@ __device__ __forceinline__ void rd_row(typename R::Loc &loc, const T *row, int64
   if constexpr (!BAD) rd_row_k<R, T, 0>(loc, row, lo, hi, inc, lane, width, abad);
   else if constexpr (rd_kbadident<R>::value) {
     if (abad == R::identity()) rd_row_k<R, T, 3>(loc, row, lo, hi, inc, lane, width, abad);
+    else if (abad == R::anti_identity()) rd_row_k<R, T, 4>(loc, row, lo, hi, inc, lane, width, abad);
     else rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad);
   }
   else if constexpr (tt<T>::is_int) rd_row_k<R, T, 1>(loc, row, lo, hi, inc, lane, width, abad);
