@@ -8,10 +8,11 @@
 //    take 32 consecutive elements per step.  Integer results are bit-exact (wrap-around add/multiply
 //    is associative); float results differ from the sequential order only in rounding.
 //    - long rows, many of them: one chunk = the whole row, no carry-in.
-//    - few very long rows (a 1-D cumusumover is the common case): three passes over chunks of a
-//      multiple of SC_CHUNK elements sized for one resident wave of warps: (1) chunk totals,
-//      (2) scan_chunk_prefix_kernel: exclusive scan of the totals per row, (3) the scan again with
-//      the chunk's carry-in.  3 passes of traffic instead of the ideal 2, but every SM works on the row.
+//    - few very long rows (a 1-D cumusumover is the common case): scan_onepass_kernel (scan_onepass.cuh) — one
+//      pass, decoupled look-back, bulk-async tiles — when T and O have the same size and the rows are 16-byte
+//      aligned; otherwise three passes over chunks of a multiple of SC_CHUNK elements sized for one resident
+//      wave of warps: (1) chunk totals, (2) scan_chunk_prefix_kernel: exclusive scan of the totals per row,
+//      (3) the scan again with the chunk's carry-in.  3 passes of traffic instead of the ideal 2.
 #include <cstdio>
 #include <cstring>
 #include "common.cuh"
