@@ -8,7 +8,7 @@
 namespace pdlb200 {
 
 int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_t acc_size,
-                  RdPlan *p, RdLaunch *l, const Err &E) {
+                  RdPlan *p, RdLaunch *l, const Err &E, bool heavy_row_end) {
   if (t->npdls != 2)
     return E.fail(PDLB200_EINVAL, "%s: expected 2 parameters, got %d", pdlb200_op_name(t->op), t->npdls);
   if (t->ind[0] < 0) return E.fail(PDLB200_EINVAL, "%s: size of dim n is %lld", pdlb200_op_name(t->op), (long long)t->ind[0]);
@@ -41,7 +41,19 @@ int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_
   const bool column = (p->inc_n != 1 || n <= 1) && (p->sa[0] == 1 || p->sa[0] == -1) && p->dims[0] >= 32;
   int mode;
   if (column) mode = 0;
-  else if ((int64_t)n * (int64_t)in_size >= 32768) mode = 2;
+  else if ((int64_t)n * (int64_t)in_size >= 32768) {
+    mode = 2;
+    if (heavy_row_end) {
+      // min/max reducers end every row with a tree over (value, index, state) records and a re-walk test: a CTA needs
+      // several trips per thread to amortise it (measured, float rows: 32 KB rows 0.81 CTA-per-row vs 1.02
+      // warp-per-row; 64 KB rows of cfg2 0.98 vs 1.03).  Warp-per-row only while every resident warp gets (almost)
+      // the same number of rows — otherwise the last wave costs more than the row ends save.
+      const int64_t row_bytes = (int64_t)n * (int64_t)in_size;
+      const double r = (double)p->nrows / (double)((int64_t)sms * 8 * (RD_THREADS / 32));   // rows per resident warp
+      if (row_bytes < 65536) { if (r >= 0.5) mode = 1; }
+      else if (row_bytes <= 262144) { if (r >= 1.0 && (double)(int64_t)(r + 0.999999) / r <= 1.03) mode = 1; }
+    }
+  }
   else if (n >= 64) mode = 1;
   else mode = 0;
   if (const char *e = getenv("PDLB200_REDUCE_MODE")) { int m = atoi(e); if (m >= 0 && m <= 2) mode = m; }
