@@ -820,12 +820,12 @@ reduce_finish_kernel(const __grid_constant__ RdPlan p, const int cta_per_row) {
 // host planner (reduce_plan.cu)
 struct RdLaunch { int mode; dim3 grid; };
 int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_t acc_size,
-                  RdPlan *p, RdLaunch *l, const Err &E, bool heavy_row_end = false);
+                  RdPlan *p, RdLaunch *l, const Err &E, bool heavy_row_end = false, int blocks_per_sm = 8);
 
 template <class R, class T, class O>
 int rd_launch_typed(const pdlb200_trans *t, const char *name, const Err &E) {
   RdPlan p; RdLaunch l;
-  int rc = rd_build_plan(t, sizeof(T), sizeof(O), sizeof(typename R::Acc), &p, &l, E, R::kRescan);
+  int rc = rd_build_plan(t, sizeof(T), sizeof(O), sizeof(typename R::Acc), &p, &l, E, R::kRescan, rd_min_blocks<R>());
   if (rc) return rc;
   if (p.nrows == 0) return PDLB200_OK;
   cudaStream_t s = (cudaStream_t)t->stream;

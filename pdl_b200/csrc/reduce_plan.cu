@@ -8,7 +8,7 @@
 namespace pdlb200 {
 
 int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_t acc_size,
-                  RdPlan *p, RdLaunch *l, const Err &E, bool heavy_row_end) {
+                  RdPlan *p, RdLaunch *l, const Err &E, bool heavy_row_end, int blocks_per_sm) {
   if (t->npdls != 2)
     return E.fail(PDLB200_EINVAL, "%s: expected 2 parameters, got %d", pdlb200_op_name(t->op), t->npdls);
   if (t->ind[0] < 0) return E.fail(PDLB200_EINVAL, "%s: size of dim n is %lld", pdlb200_op_name(t->op), (long long)t->ind[0]);
@@ -60,11 +60,14 @@ int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_
 
   const int64_t rows_per_cta = mode == 0 ? RD_THREADS : mode == 1 ? RD_THREADS / 32 : 1;
   int64_t ctas = (p->nrows + rows_per_cta - 1) / rows_per_cta;
-  const int64_t target = (int64_t)sms * 8;
-  // too few row-CTAs: cut n into chunks (>= 16K elements each so the partial traffic stays negligible)
+  // the CTAs that are resident at once (launch bounds: 8 per SM for the light reducers, 5 for the heavy ones)
+  const int64_t target = (int64_t)sms * (blocks_per_sm > 0 ? blocks_per_sm : 8);
+  // too few row-CTAs: cut n into chunks (>= 16K elements each so the partial traffic stays negligible).  The grid must
+  // not spill into a second, nearly empty wave — 64 rows x 19 chunks = 1216 CTAs on 1184 slots ran at 0.80 of peak,
+  // the last 32 CTAs alone on the machine — so the chunk count is rounded DOWN to what is resident at once.
   const int64_t min_chunk = mode == 0 ? 256 : 16384;
   if (ctas < target / 2 && n >= 2 * min_chunk) {
-    int64_t want = (target + ctas - 1) / ctas;
+    int64_t want = target / ctas;
     int64_t maxc = n / min_chunk;
     if (want > maxc) want = maxc;
     if (want > 65535) want = 65535;
@@ -94,7 +97,9 @@ int rd_build_plan(const pdlb200_trans *t, size_t in_size, size_t out_size, size_
                                    pdlb200_op_name(t->op), (size_t)p->nrows * p->nchunks * acc_size);
   }
   int64_t gx = ctas;
-  const int64_t cap = (target + p->nchunks - 1) / p->nchunks;
+  // whole rows: up to 8 CTAs per SM in the grid even when fewer are resident (the queued ones even out the end of the
+  // launch); rows cut into chunks: exactly what is resident
+  const int64_t cap = p->nchunks > 1 ? target / p->nchunks : (int64_t)sms * 8;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   l->mode = mode;
   l->grid = dim3((unsigned)gx, (unsigned)p->nchunks, 1);
