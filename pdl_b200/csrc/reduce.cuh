@@ -146,16 +146,60 @@ template <class T, class O> struct RSum {
 // the zero comes from the prefix only, and an inf/NaN prefix gives NaN (inf*0) which never compares
 // equal to 0, so the loop runs on and stays NaN.  z is reduced here (min); the kernel then runs a
 // second pass over [0, z) for rows that have one (kPrefix).
+// The loop ALSO stops when the running product underflows to zero before any zero element ([1e-200, 1e-200, inf] is 0
+// in the reference; a product taken in another order is NaN, or finite).  That depends on the sequential order, so the
+// reducer only detects that it CAN happen, in two steps.  Hot loop (3 integer instructions per element): the smallest
+// non-zero magnitude of the row; n * min(0, floor(log2 of it)) bounds every prefix product from below, and rows of
+// factors >= 1 never get past this test.  Rows that do are summed again by the group with
+// negl = sum of min(0, log2|a|) (RNegLog, one MUFU per element): 2^negl is the tight bound.  Only rows whose tight
+// bound reaches the subnormal range are recomputed by one thread in the reference's order (rd_prod_sequential) —
+// which stops early exactly where the reference does.
+template <class T> __device__ __forceinline__ float neg_log2_abs(T v) {
+  if constexpr (tt<T>::is_int) return 0.0f;
+  else if constexpr (sizeof(T) == 4) {
+    const float a = fabsf(v);
+    return (a < 1.0f && a != 0.0f) ? __log2f(a) : 0.0f;
+  } else {
+    const double a = fabs(v);
+    if (!(a < 1.0) || a == 0.0) return 0.0f;
+    const int hi = __double2hiint(a), e = (hi >> 20) & 0x7ff;
+    if (e == 0) return -1100.0f;                                     // subnormal: straight into the recomputed class
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(a));   // [1, 2)
+    return (float)(e - 1023) + __log2f((float)m);
+  }
+}
+// magnitude key of a float/double: monotonic in |v| over the non-zero values, zero -> 0xffffffff (never the minimum)
+template <class T> __device__ __forceinline__ uint32_t mag_key(T v, bool is_zero) {
+  if constexpr (tt<T>::is_int) return 0xffffffffu;
+  else if constexpr (sizeof(T) == 4) return (__float_as_uint(v) & 0x7fffffffu) - (uint32_t)is_zero;
+  else return ((uint32_t)__double2hiint(v) & 0x7fffffffu) - (uint32_t)is_zero;   // a subnormal below 2^-1042: key 0, the smallest
+}
 template <class T, class O> struct RProd {
   static constexpr bool kPrefix = !tt<O>::is_int;
+  static constexpr bool kUnderflow = kPrefix && !tt<T>::is_int;      // integer factors are 0 or >= 1 in magnitude
   static constexpr bool kRescan = false;
   static constexpr int kUnroll = (sizeof(O) <= 4 && tt<O>::is_int) ? 4 : 8;
-  struct Loc { O s; int32_t any; int32_t z; };
-  struct Acc { O s; int32_t any; int32_t pad; int64_t z; };
-  static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(1); x.any = 0; x.z = 0x7fffffff; return x; }
+  struct Loc { O s; int32_t any; int32_t z; uint32_t mkey; };
+  struct Acc { O s; int32_t any; uint32_t mkey; int64_t z; };
+  static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(1); x.any = 0; x.z = 0x7fffffff; x.mkey = 0xffffffffu; return x; }
   static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t rel) {
     x.s = wrap_mul<O>(x.s, (O)v); x.any = 1;
-    if constexpr (kPrefix) { if ((O)v == O(0) && rel < x.z) x.z = rel; }
+    if constexpr (kPrefix) {
+      const bool zero = (O)v == O(0);
+      if (zero && rel < x.z) x.z = rel;
+      if constexpr (kUnderflow) { const uint32_t k = mag_key<T>(v, zero); x.mkey = k < x.mkey ? k : x.mkey; }
+    }
+  }
+  // binades below which a product is zero, less a margin for the approximate logarithms of the second step
+  static constexpr float kZeroLog2 = sizeof(O) == 4 ? -137.0f : -1060.0f;
+  // step 1: can n factors no smaller than the row's smallest one underflow?
+  static __device__ __forceinline__ bool may_underflow(const Acc &x, int64_t n) {
+    if constexpr (!kUnderflow) return false;
+    else {
+      if (x.mkey == 0xffffffffu) return false;                      // no non-zero factor at all
+      const int e = sizeof(T) == 4 ? (int)(x.mkey >> 23) - 127 : (int)(x.mkey >> 20) - 1023;   // floor(log2 min|a|)
+      return e < 0 && (float)n * (float)e <= kZeroLog2;
+    }
   }
   // 8/16-bit integers into a 32-bit product: BAD lanes are replaced by 1 on whole words (no per-element compare /
   // branch), then one multiply per lane
@@ -176,11 +220,11 @@ template <class T, class O> struct RProd {
     x.any |= (nbad != (int32_t)(16 / sizeof(T)));
   }
   static __device__ __forceinline__ Acc lift(const Loc &l, int64_t lo) {
-    Acc x; x.s = l.s; x.any = l.any; x.pad = 0; x.z = (l.z == 0x7fffffff) ? RD_NOIDX : lo + l.z; return x;
+    Acc x; x.s = l.s; x.any = l.any; x.mkey = l.mkey; x.z = (l.z == 0x7fffffff) ? RD_NOIDX : lo + l.z; return x;
   }
-  static __device__ __forceinline__ Acc init() { Acc x; x.s = O(1); x.any = 0; x.pad = 0; x.z = RD_NOIDX; return x; }
+  static __device__ __forceinline__ Acc init() { Acc x; x.s = O(1); x.any = 0; x.mkey = 0xffffffffu; x.z = RD_NOIDX; return x; }
   static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) {
-    Acc x; x.s = wrap_mul<O>(l.s, r.s); x.any = l.any | r.any; x.pad = 0; x.z = l.z < r.z ? l.z : r.z; return x;
+    Acc x; x.s = wrap_mul<O>(l.s, r.s); x.any = l.any | r.any; x.mkey = l.mkey < r.mkey ? l.mkey : r.mkey; x.z = l.z < r.z ? l.z : r.z; return x;
   }
   static __device__ __forceinline__ void finish(const Acc &x, const RdPlan &p, O *out) {
     *out = (p.badmode && !x.any) ? from_bits<O>(p.bbad) : x.s;
@@ -704,6 +748,48 @@ __device__ __forceinline__ typename R::Acc rd_group_reduce(typename R::Acc acc, 
   return acc;
 }
 
+// prodover in the reference's own order (Ufunc.pd:102-110), by ONE thread: for the rows RProd::may_underflow flags
+template <class T, class O, bool BAD>
+__device__ __noinline__ O rd_prod_sequential(const T *row, int64_t n, int64_t inc, T abad, bool abadnan, O bbad) {
+  O tmp = O(1);
+  bool flag = false;
+  for (int64_t i = 0; i < n; i++) {
+    const T v = row[i * inc];
+    if (BAD && is_bad(v, abad, abadnan)) continue;
+    flag = true;
+    tmp = tmp * (O)v;
+    if (tmp == O(0)) break;
+  }
+  return (BAD && !flag) ? bbad : tmp;
+}
+
+// step 2 of the underflow test: negl = sum of min(0, log2|a|) over the good non-zero elements of the row, by the group
+template <class T> struct RNegLog {
+  static constexpr bool kPrefix = false;
+  static constexpr bool kRescan = false;
+  static constexpr int kUnroll = 4;
+  struct Acc { float s; int32_t any; };
+  using Loc = Acc;
+  static __device__ __forceinline__ Acc init() { Acc x; x.s = 0.0f; x.any = 0; return x; }
+  static __device__ __forceinline__ Loc linit() { return init(); }
+  static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s += neg_log2_abs<T>(v); }
+  static __device__ __forceinline__ Acc lift(const Loc &l, int64_t) { return l; }
+  static __device__ __forceinline__ Acc merge(const Acc &l, const Acc &r) { Acc x; x.s = l.s + r.s; x.any = 0; return x; }
+};
+template <class T, bool BAD, int MODE>
+__device__ __forceinline__ float rd_neg_log(const T *row, int64_t n, int64_t inc, int lane, int width, T abad, bool abadnan, void *smem) {
+  using P = RNegLog<T>;
+  typename P::Acc tot = P::init();
+  for (int64_t lo = 0; lo < n; lo += 0x40000000ll) {
+    const int64_t hi = (lo + 0x40000000ll < n) ? lo + 0x40000000ll : n;
+    typename P::Loc loc = P::linit();
+    rd_row<P, T, BAD>(loc, row, lo, hi, inc, lane, width, abad, abadnan);
+    tot = P::merge(tot, loc);
+  }
+  tot = rd_group_reduce<P, MODE>(tot, reinterpret_cast<typename P::Acc *>(smem));
+  return tot.s;
+}
+
 // prodover second phase: the product of the good elements of [0, z) times a[z], by the group.
 template <class R, class T, class O, bool BAD, int MODE>
 __device__ __forceinline__ O rd_prod_prefix(const T *row, int64_t z, int64_t inc, int lane, int width,
@@ -767,7 +853,13 @@ reduce_rows_kernel(const __grid_constant__ RdPlan p) {
         continue;
       }
       if constexpr (R::kPrefix) {
-        if (acc.z != RD_NOIDX) {   // uniform over the group: every thread holds the total
+        if (R::may_underflow(acc, p.n)) {   // uniform over the group: every thread holds the total
+          if (rd_neg_log<T, BAD, MODE>(rp, p.n, p.inc_n, lane, width, abad, abadnan, smem) <= R::kZeroLog2) {
+            if (writer) *out = rd_prod_sequential<T, O, BAD>(rp, p.n, p.inc_n, abad, abadnan, from_bits<O>(p.bbad));
+            continue;
+          }
+        }
+        if (acc.z != RD_NOIDX) {
           const O v = rd_prod_prefix<R, T, O, BAD, MODE>(rp, acc.z, p.inc_n, lane, width, abad, abadnan, smem);
           if (writer) *out = v;
           continue;
@@ -803,6 +895,15 @@ reduce_finish_kernel(const __grid_constant__ RdPlan p, const int cta_per_row) {
     }
     O *out = reinterpret_cast<O *>(p.b) + ob;
     if constexpr (R::kPrefix) {
+      if (R::may_underflow(acc, p.n)) {
+        const T *rp = reinterpret_cast<const T *>(p.a) + oa;
+        const float negl = cta_per_row ? rd_neg_log<T, BAD, 2>(rp, p.n, p.inc_n, lane, width, from_bits<T>(p.abad), p.abadnan != 0, smem)
+                                       : rd_neg_log<T, BAD, 1>(rp, p.n, p.inc_n, lane, 32, from_bits<T>(p.abad), p.abadnan != 0, nullptr);
+        if (negl <= R::kZeroLog2) {
+          if (lane == 0) *out = rd_prod_sequential<T, O, BAD>(rp, p.n, p.inc_n, from_bits<T>(p.abad), p.abadnan != 0, from_bits<O>(p.bbad));
+          continue;
+        }
+      }
       if (acc.z != RD_NOIDX) {
         const T *rp = reinterpret_cast<const T *>(p.a) + oa;
         O v;

@@ -206,6 +206,35 @@ def test_float_sum_tolerance(engines):
             assert np.all(np.abs(g - w) <= bound), (op, T.NAMES[t], np.max(np.abs(g - w) / bound))
 
 
+@pytest.mark.parametrize("t", [T.F, T.D], ids=lambda t: T.NAMES[t])
+def test_prodover_stops_when_the_running_product_underflows(engines, t):
+    """`tmp *= a; if (tmp == 0) break;` (Ufunc.pd:102-110) also stops when the RUNNING product underflows to zero,
+    which depends on the sequential order: [tiny, tiny, inf] is 0 in the reference.  Factors are powers of two, so every
+    product is exact in any order until it leaves the representable range — the device must agree bit for bit (sign of
+    the zero included), for every cooperation width, with BAD values, for dprodover, and rows that never get near the
+    subnormal range must not be touched by the sequential path (same answer either way)."""
+    rng = np.random.default_rng(1700 + t)
+    dt = T.NP_DTYPE[t]
+    dt = np.dtype(dt).type
+    tiny = dt(2.0) ** (-100 if t == T.F else -800)
+    for op in ("prodover", "dprodover"):
+        a = np.array([[tiny, tiny, np.inf, 3.0], [tiny, -tiny, 0.0, np.inf], [2.0, 0.5, 4.0, 0.25]], dtype=dt)
+        (ga, oa) = both(engines, a, t)
+        assert_same(f"{op}-underflow-small-{T.NAMES[t]}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa))
+        for n, rows in ((5000, 40), (70_000, 6), (300, 500), (40, 3000)):
+            k = rng.integers(-40, 12, size=(rows, n))                         # drifts down: most rows underflow somewhere
+            k[::3] = rng.integers(-3, 4, size=k[::3].shape)                   # every third row stays in range
+            a = (dt(2.0) ** k.astype(dt)) * rng.choice(np.array([-1.0, 1.0], dtype=dt), size=k.shape)
+            a[rng.random(a.shape) < 0.001] = np.inf                           # poison after the underflow point
+            for bad in (False, True):
+                src = a.copy()
+                if bad:
+                    src[rng.random(src.shape) < 0.02] = np.array(T.DEFAULT_BAD[t]).astype(dt)
+                (ga, oa) = both(engines, src, t, bad)
+                assert_same(f"{op}-underflow-{T.NAMES[t]}-{n}x{rows}-bad{int(bad)}", getattr(ufunc, op)(ga), getattr(ufunc, op)(oa),
+                            nan_equal=True)
+
+
 @pytest.mark.parametrize("t", ALL_TYPES, ids=lambda t: T.NAMES[t])
 def test_matmult_exact_kernel(engines, t):
     rng = np.random.default_rng(1200 + t)
