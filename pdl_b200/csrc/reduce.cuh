@@ -190,6 +190,14 @@ template <class T, class O> struct RProd {
       if constexpr (kUnderflow) { const uint32_t k = mag_key<T>(v, zero); x.mkey = k < x.mkey ? k : x.mkey; }
     }
   }
+  // BAD mode without a branch: a BAD element is the factor 1 (never zero, never the smallest magnitude below 1)
+  static constexpr bool kPushSel = kUnderflow;
+  static __device__ __forceinline__ void lpush_sel(Loc &x, T v, int32_t rel, bool bad) {
+    const T w = bad ? T(1) : v;
+    const int32_t any = x.any | (int32_t)!bad;
+    lpush(x, w, rel);
+    x.any = any;
+  }
   // binades below which a product is zero, less a margin for the approximate logarithms of the second step
   static constexpr float kZeroLog2 = sizeof(O) == 4 ? -137.0f : -1060.0f;
   // step 1: can n factors no smaller than the row's smallest one underflow?
@@ -557,8 +565,17 @@ template <class T, bool GOOD> struct RCount {
 template <class R, class = void> struct rd_kbadident { static constexpr bool value = false; };
 template <class R> struct rd_kbadident<R, std::void_t<decltype(R::kBadIdentity)>> { static constexpr bool value = R::kBadIdentity; };
 
+// reducers whose per-element body is long enough that skipping it with a branch costs more than running it on a
+// neutral element: `lpush_sel(loc, v, rel, bad)`
+template <class R, class = void> struct rd_kpushsel : std::false_type {};
+template <class R> struct rd_kpushsel<R, std::void_t<decltype(R::kPushSel)>> : std::integral_constant<bool, R::kPushSel> {};
+
 template <class R, class T, int BADK>
 __device__ __forceinline__ void rd_push(typename R::Loc &loc, T v, int32_t rel, T abad) {
+  if constexpr (rd_kpushsel<R>::value && (BADK == 1 || BADK == 2)) {
+    R::lpush_sel(loc, v, rel, BADK == 1 ? (v == abad) : t_isnan(v));
+    return;
+  }
   if constexpr (BADK == 1 || BADK == 3 || BADK == 4) { if (v == abad) return; }
   if constexpr (BADK == 2) { if (t_isnan(v)) return; }
   R::lpush(loc, v, rel);
