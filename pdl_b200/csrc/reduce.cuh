@@ -118,6 +118,12 @@ template <class T, class O> struct RSum {
   struct Acc { O s; int32_t any; int32_t pad; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.any = 0; return x; }
   static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.any = 1; }
+  // 64-bit integer sums in BAD mode: add 0 for a BAD element instead of branching around the add (the branch kept the
+  // compiler from holding the trip's loads in flight: 0.80 of peak)
+  static constexpr bool kPushSel = tt<O>::is_int && sizeof(O) == 8;
+  static __device__ __forceinline__ void lpush_sel(Loc &x, T v, int32_t, bool bad) {
+    x.s = wrap_add<O>(x.s, bad ? O(0) : (O)v); x.any |= (int32_t)!bad;
+  }
   // 8/16-bit integers into a 32-bit sum: a whole 16-byte image at a time (see swar_* above)
   static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2 && std::is_same<O, int32_t>::value;
   template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
@@ -248,6 +254,10 @@ template <class T, class O> struct RAvg {
   struct Acc { O s; int64_t cnt; };
   static __device__ __forceinline__ Loc linit() { Loc x; x.s = O(0); x.cnt = 0; return x; }
   static __device__ __forceinline__ void lpush(Loc &x, T v, int32_t) { x.s = wrap_add<O>(x.s, (O)v); x.cnt++; }
+  static constexpr bool kPushSel = tt<O>::is_int && sizeof(O) == 8;
+  static __device__ __forceinline__ void lpush_sel(Loc &x, T v, int32_t, bool bad) {
+    x.s = wrap_add<O>(x.s, bad ? O(0) : (O)v); x.cnt += (int32_t)!bad;
+  }
   static constexpr bool kPack = tt<T>::is_int && sizeof(T) <= 2 && std::is_same<O, int32_t>::value;
   template <int BADK> static __device__ __forceinline__ void lpush_pack(Loc &x, const Pack<T> &r, T abad) {
     const uint32_t badw = swar_splat<T>(abad);
