@@ -92,6 +92,12 @@ template <class T> __device__ __forceinline__ uint32_t swar_eq_mask(uint32_t w, 
     return (hi >> 15) * 0xffffu;
   }
 }
+// number of lanes of w equal to the lane of badw (the zero-lane test of swar_eq_mask without building the mask)
+template <class T> __device__ __forceinline__ int32_t swar_eq_count(uint32_t w, uint32_t badw) {
+  const uint32_t x = w ^ badw;
+  if constexpr (sizeof(T) == 1) return __popc(~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);
+  else return __popc(~(((x & 0x7fff7fffu) + 0x7fff7fffu) | x) & 0x80008000u);
+}
 // acc + sum of the lanes of w (lanes read as T), wrapping in 32 bits
 template <class T> __device__ __forceinline__ int32_t swar_sum(uint32_t w, int32_t acc) {
   if constexpr (sizeof(T) == 1) {
@@ -130,12 +136,13 @@ template <class T, class O> struct RSum {
     const uint32_t badw = swar_splat<T>(abad);
     const uint32_t w[4] = {r.q.x, r.q.y, r.q.z, r.q.w};
     int32_t nbad = 0, s = (int32_t)x.s;
+    // BAD lanes are summed like the others and taken out again as badvalue x (number of BAD lanes): no mask
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      uint32_t g = w[i];
-      if constexpr (BADK == 1) g &= ~swar_eq_mask<T>(g, badw, nbad);
-      s = swar_sum<T>(g, s);
+      if constexpr (BADK == 1) nbad += swar_eq_count<T>(w[i], badw);
+      s = swar_sum<T>(w[i], s);
     }
+    if constexpr (BADK == 1) s -= (int32_t)abad * nbad;
     x.s = (O)s;
     x.any |= (nbad != (int32_t)(16 / sizeof(T)));
   }
@@ -265,10 +272,10 @@ template <class T, class O> struct RAvg {
     int32_t nbad = 0, s = (int32_t)x.s;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      uint32_t g = w[i];
-      if constexpr (BADK == 1) g &= ~swar_eq_mask<T>(g, badw, nbad);
-      s = swar_sum<T>(g, s);
+      if constexpr (BADK == 1) nbad += swar_eq_count<T>(w[i], badw);
+      s = swar_sum<T>(w[i], s);
     }
+    if constexpr (BADK == 1) s -= (int32_t)abad * nbad;
     x.s = (O)s;
     x.cnt += (int32_t)(16 / sizeof(T)) - nbad;
   }
