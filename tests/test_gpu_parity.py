@@ -739,6 +739,21 @@ def test_small_int_divide_sqrt_exhaustive(engines, t):
     assert_same(f"sqrt-exhaustive-{T.NAMES[t]}", P.run_ufunc("sqrt", gv), P.run_ufunc("sqrt", ov))
 
 
+@pytest.mark.parametrize("t", [T.L, T.UL] if hasattr(T, "UL") else [T.L], ids=lambda t: T.NAMES[t])
+def test_int32_sqrt_float_root_plus_integer_checks(engines, t):
+    """32-bit integer sqrt = float root corrected by two integer checks: every perfect square and its two neighbours up
+    to the type's maximum, the maximum itself, random values — against the oracle's (T)sqrt((double)a)."""
+    dt = T.NP_DTYPE[t]
+    hi = np.iinfo(dt).max
+    k = np.arange(0, int(np.sqrt(float(hi))) + 1, dtype=np.int64)
+    v = np.concatenate([k * k - 1, k * k, k * k + 1, [hi, hi - 1, 0, 1, 2, 3]])
+    v = v[(v >= 0) & (v <= hi)]
+    rng = np.random.default_rng(1800 + t)
+    v = np.concatenate([v, rng.integers(0, hi, size=200_000, dtype=np.int64)]).astype(dt)
+    (gv, ov) = both(engines, v, t)
+    assert_same(f"sqrt-int32-{T.NAMES[t]}", P.run_ufunc("sqrt", gv), P.run_ufunc("sqrt", ov))
+
+
 def test_cabi_error_returns_on_device(cuda_engine):
     """Malformed descriptors come back as error codes + messages through the C-ABI, never as a crash or a
     silently wrong launch: missing `anybad` for the ops that need it, wrong fixed parameter types, a type
