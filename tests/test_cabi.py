@@ -27,6 +27,32 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_abi.Trans) == 6 * 4 + 16 * 8 + 80 * 8 + 4 * 8 + 8 * 8 + 5 * C.sizeof(_abi.Par) + 8 + 8 + 8
 
 
+def test_field_offsets_match_a_c_compiler(tmp_path):
+    """offsetof() of every descriptor field as gcc lays out include/pdlb200.h against the ctypes mirror (_abi.py):
+    a renamed or re-ordered field shows up here, not as a wrong answer on the device."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    fields = {"pdlb200_trans": [n for n, _ in _abi.Trans._fields_], "pdlb200_par": [n for n, _ in _abi.Par._fields_]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pdlb200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        for n in names:
+            lines.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+        lines.append(f'  printf("{st}.sizeof %zu\\n", sizeof({st}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "offsets"
+    root = __import__("pathlib").Path(__file__).resolve().parent.parent
+    subprocess.run(["gcc", "-I", str(root / "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for st, cls in (("pdlb200_trans", _abi.Trans), ("pdlb200_par", _abi.Par)):
+        for n, _ in cls._fields_:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)
+        assert int(got[f"{st}.sizeof"]) == C.sizeof(cls), st
+
+
 def test_plumbing_without_gpu():
     lib = _abi.load()
     assert lib.pdlb200_abi_version() == _abi.ABI_VERSION == 4
