@@ -42,6 +42,15 @@ elif op == "matmult_exact_float":
     n = 4096
     A, B, Cc = (torch.randint(-8, 8, (n, n), device=dev).float() for _ in range(3))
     f = P.prepare_op("matmult", [wrap(A, T.F, [n, n]), wrap(B, T.F, [n, n])], [wrap(Cc, T.F, [n, n])])
+elif op == "matmult_2048":          # 256 tiles on 148 SMs: the stream-K persistent kernel
+    n = 2048
+    A, B, Cc = (torch.rand((n, n), dtype=torch.float64, device=dev) for _ in range(3))
+    f = P.prepare_op("matmult", [wrap(A, T.D, [n, n]), wrap(B, T.D, [n, n])], [wrap(Cc, T.D, [n, n])])
+elif op == "matmult_exact_bad_double":
+    n = 4096
+    A, B, Cc = (torch.randint(-64, 64, (n, n), device=dev).double() / 64 for _ in range(3))
+    A[17, 33] = -1.7976931348623157e308
+    f = P.prepare_op("matmult", [wrap(A, T.D, [n, n]).set_badflag(True), wrap(B, T.D, [n, n])], [wrap(Cc, T.D, [n, n])])
 elif op == "matmult":
     n = 4096
     A, B, Cc = (torch.rand((n, n), dtype=torch.float64, device=dev) for _ in range(3))
